@@ -1,0 +1,161 @@
+/*
+ * uwvkf -- C ABI of the B200-native batched manifold-UKF engine.
+ *
+ * Drop-in boundary for the filter classes of tomcreutz/slam-uwv_kalman_filters.  The reference has no FFI
+ * layer: its operator API for the hot path is the C++ class interface (predictionStep(dt) /
+ * integrateMeasurement(...) / getters) on top of ukfom::ukf<State>::predict(g, Q) / update(z, h, R, gate),
+ * which take host callables (reference src/PoseUKF.cpp:462-465, 479-481).  Host callables cannot run on a
+ * GPU, so the seam sits at the filter-class level: the process / measurement models are compiled into the
+ * kernels and selected by enum.  Each entry point cites the reference interface it replaces.  One handle
+ * owns a BATCH of independent filters of one class on one device; batch = 1 is the reference's object.
+ *
+ * Conventions: plain pointers and sizes only; every call returns UWVKF_OK (0) or a negative error code
+ * and never throws; uwvkf_last_error() returns a thread-local message.  Calls are asynchronous on the
+ * handle's stream unless they return data to the host.  A handle is not thread-safe; distinct handles
+ * are independent.  There is NO CPU fallback: without a CUDA device uwvkf_create fails with
+ * UWVKF_ERR_NO_DEVICE.
+ *
+ * Layouts (host side, row-major, per filter, filters contiguous):
+ *   PoseUKF      mu[54]  = p(3) q(x,y,z,w) v(3) a(3) b_gyro(3) b_acc(3) g inertia(9,col-major 3x3)
+ *                          lin_damping(9) quad_damping(9) water_velocity(2) water_velocity_below(2)
+ *                          bias_adcp(2) water_density            (reference src/PoseState.hpp:29-45)
+ *                cov[53*53], tangent order = declaration order, orientation = 3 DOF at 3..5
+ *   VelocityUKF  mu[4] = v(3) z ; cov[4*4]                       (src/VelocityUKF.hpp:24-27)
+ *   BottomUKF    mu[4] = distance, normal(3, unit) ; cov[3*3]    (src/BottomUKF.hpp:18-21)
+ *   IndirectPoseUKF mu[7] = position_error(3) q(x,y,z,w) ; cov[6*6] (src/IndirectPoseUKF.hpp:19-22)
+ */
+#ifndef UWVKF_H
+#define UWVKF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uwvkf_filter_s *uwvkf_handle;
+
+enum uwvkf_filter_kind {
+  UWVKF_FILTER_POSE = 0,          /* uwv_kalman_filters::PoseUKF          src/PoseUKF.hpp:40 */
+  UWVKF_FILTER_VELOCITY = 1,      /* uwv_kalman_filters::VelocityUKF      src/VelocityUKF.hpp:33 */
+  UWVKF_FILTER_BOTTOM = 2,        /* uwv_kalman_filters::BottomUKF        src/BottomUKF.hpp:27 */
+  UWVKF_FILTER_INDIRECT_POSE = 3  /* uwv_kalman_filters::IndirectPoseUKF  src/IndirectPoseUKF.hpp:29 */
+};
+
+enum uwvkf_error {
+  UWVKF_OK = 0,
+  UWVKF_ERR_INVALID_ARGUMENT = -1,
+  UWVKF_ERR_NO_DEVICE = -2,        /* no CUDA device / driver: the engine has no CPU path */
+  UWVKF_ERR_CUDA = -3,
+  UWVKF_ERR_NAN_MEASUREMENT = -4,  /* checkMeasurment() of the reference base class would have thrown */
+  UWVKF_ERR_NOT_INITIALIZED = -5,  /* e.g. "Motion model is not initialized!" src/VelocityUKF.cpp:117-118 */
+  UWVKF_ERR_UNSUPPORTED = -6
+};
+
+enum uwvkf_memspace { UWVKF_HOST = 0, UWVKF_DEVICE = 1 };
+
+/* per-filter asynchronous status bits (uwvkf_get_status) */
+enum uwvkf_status_bits {
+  UWVKF_ST_NOT_SPD = 1u,            /* Cholesky met a non-positive pivot: op skipped, filter left untouched */
+  UWVKF_ST_NAN_MEASUREMENT = 2u,    /* device-side NaN check refused a measurement */
+  UWVKF_ST_GATE_REJECTED = 4u,      /* innovation gate (d2p95) refused at least one update */
+  UWVKF_ST_MEAN_NOT_CONVERGED = 8u  /* iterated manifold mean hit max_it */
+};
+
+/* PoseUKF measurement kinds: one per integrateMeasurement overload (src/PoseUKF.hpp:137-177) */
+enum uwvkf_pose_meas {
+  UWVKF_POSE_XY = 0,             /* XY_Position m=2                              src/PoseUKF.cpp:506-512 */
+  UWVKF_POSE_Z = 1,              /* Z_Position m=1                               src/PoseUKF.cpp:498-504 */
+  UWVKF_POSE_PRESSURE = 2,       /* Pressure m=1, aux = pressure_sensor_in_imu[3] src/PoseUKF.cpp:559-565 */
+  UWVKF_POSE_ACCELERATION = 3,   /* Acceleration m=3                             src/PoseUKF.cpp:484-490 */
+  UWVKF_POSE_VELOCITY = 4,       /* Velocity (DVL) m=3                           src/PoseUKF.cpp:476-482 */
+  UWVKF_POSE_WATER_VELOCITY = 5, /* ADCP m=2, aux = cell_weighting, gate d2p95   src/PoseUKF.cpp:604-611 */
+  UWVKF_POSE_GEOGRAPHIC = 6,     /* lat/lon [rad] m=2, aux = gps_in_body[3], d2p95 src/PoseUKF.cpp:567-579 */
+  UWVKF_POSE_DELAYED_XY = 7      /* m=2, aux = delayed_position[2]               src/PoseUKF.cpp:514-527 */
+};
+
+#define UWVKF_POSE_DIM 54
+#define UWVKF_POSE_DOF 53
+#define UWVKF_POSE_NPARAMS 22
+#define UWVKF_POSE_NOFFSETS 28
+
+/* flat PoseUKF::PoseUKFParameter (src/PoseUKF.hpp:46-76) preceded by the projection origin that the
+ * reference keeps in its GeographicProjection member (src/PoseUKF.cpp:356,390) */
+enum uwvkf_pose_param_index {
+  UWVKF_PP_LAT0 = 0, UWVKF_PP_LON0 = 1, UWVKF_PP_GYRO_BIAS_TAU = 2, UWVKF_PP_GYRO_BIAS_OFFSET = 3,
+  UWVKF_PP_ACC_BIAS_TAU = 6, UWVKF_PP_ACC_BIAS_OFFSET = 7, UWVKF_PP_INERTIA_TAU = 10,
+  UWVKF_PP_LIN_DAMPING_TAU = 11, UWVKF_PP_QUAD_DAMPING_TAU = 12, UWVKF_PP_WV_TAU = 13, UWVKF_PP_WV_LIMITS = 14,
+  UWVKF_PP_WV_SCALE = 15, UWVKF_PP_ADCP_BIAS_TAU = 16, UWVKF_PP_ATM_PRESSURE = 17,
+  UWVKF_PP_WATER_DENSITY_TAU = 18, UWVKF_PP_IMU_IN_BODY = 19
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+/* Replaces the constructors (src/PoseUKF.hpp:100-115, src/VelocityUKF.hpp:42, src/BottomUKF.hpp:33,
+ * src/IndirectPoseUKF.hpp:44-48): allocates `batch` filters of `filter_kind` on CUDA device `device`. */
+int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out);
+int uwvkf_destroy(uwvkf_handle h);
+/* All work of the handle is ordered on this cudaStream_t (default: the legacy default stream). */
+int uwvkf_set_stream(uwvkf_handle h, void *cuda_stream);
+int uwvkf_synchronize(uwvkf_handle h);
+const char *uwvkf_last_error(void);
+const char *uwvkf_version(void);
+int64_t uwvkf_batch(uwvkf_handle h);
+/* kernels launched by this handle so far (bench.py's gpu_launches) */
+int64_t uwvkf_kernel_launches(uwvkf_handle h);
+
+/* ---- state ---------------------------------------------------------------------------------------- */
+/* initializeFilter(state, cov) of the base class (call sites src/PoseUKF.cpp:344,378): uploads
+ * mu[count][DIM] and the full covariances for filters [first, first+count): cov_stride = DOF*DOF for
+ * cov[count][DOF*DOF], or 0 when one covariance cov[DOF*DOF] is shared by all `count` filters.
+ * For PoseUKF it also latches the Markov offsets from the uploaded state (src/PoseUKF.cpp:346-349,385-388). */
+int uwvkf_set_state(uwvkf_handle h, const double *mu, const double *cov, int64_t cov_stride, int64_t first,
+                    int64_t count, int memspace);
+/* getCurrentState / covariance getter of the base class (used at src/VelocityUKF.cpp:70). cov may be NULL. */
+int uwvkf_get_state(uwvkf_handle h, double *mu, double *cov, int64_t first, int64_t count, int memspace);
+/* setProcessNoiseCovariance (src/PoseUKF.cpp:438): Q[DOF*DOF], shared by the batch. */
+int uwvkf_set_process_noise(uwvkf_handle h, const double *Q);
+/* ukfom mean-iteration policy: loop while |mean_delta| > tol and fewer than max_it passes (default 1e-9, 100) */
+int uwvkf_set_mean_policy(uwvkf_handle h, double tol, int max_it);
+int uwvkf_get_status(uwvkf_handle h, uint32_t *status, int64_t first, int64_t count);
+int uwvkf_clear_status(uwvkf_handle h);
+
+/* ---- PoseUKF -------------------------------------------------------------------------------------- */
+/* PoseUKFParameter + projection origin (src/PoseUKF.cpp:358-371, 356): params[UWVKF_POSE_NPARAMS], shared. */
+int uwvkf_pose_set_params(uwvkf_handle h, const double *params);
+/* Markov offsets (inertia 9, lin_damping 9, quad_damping 9, water_density) per filter, host pointer;
+ * overrides what uwvkf_set_state latched (src/PoseUKF.cpp:346-349). */
+int uwvkf_pose_set_offsets(uwvkf_handle h, const double *offsets, int64_t first, int64_t count);
+/* integrateMeasurement(const RotationRate&) (src/PoseUKF.cpp:492-496): stores the control input w[B][3]. */
+int uwvkf_pose_set_rotation_rate(uwvkf_handle h, const double *w, int memspace);
+/* getRotationRate() (src/PoseUKF.cpp:693-699) for every filter: out[B][3], host. */
+int uwvkf_pose_get_rotation_rate(uwvkf_handle h, double *out);
+/* predictionStep(dt) -> PoseUKF::predictionStepImpl (src/PoseUKF.cpp:446-466) for the whole batch. */
+int uwvkf_predict(uwvkf_handle h, double dt);
+/* integrateMeasurement(<kind>) (src/PoseUKF.cpp:476-611).  z[B][m]; R[m*m] shared or R[B][m*m] when
+ * R_per_filter != 0; aux: per-kind extra arguments shared by the batch (host pointer, may be NULL ->
+ * zeros); valid[B] (may be NULL): filters with valid == 0 skip the update (sensor dropout).
+ * memspace says where z, R (if per filter) and valid live.  NaN in a HOST z/R returns
+ * UWVKF_ERR_NAN_MEASUREMENT like checkMeasurment(); device inputs are checked per filter in the kernel. */
+int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const double *R, int R_per_filter,
+                      const double *aux, const uint8_t *valid, int memspace);
+/* Fused hot path: predictionStep(dt) immediately followed by integrateMeasurement(<kind>) in ONE kernel
+ * (one HBM round trip of the filter state).  w[B][3] is the rotation-rate control for this step (NULL:
+ * keep the stored one).  Results are identical to uwvkf_pose_set_rotation_rate + uwvkf_predict +
+ * uwvkf_pose_update. */
+int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int meas_kind, const double *z,
+                              const double *R, int R_per_filter, const double *aux, const uint8_t *valid,
+                              int memspace);
+/* resetFilterWithExternalPose (src/PoseUKF.cpp:685-691): overwrite p and q of every filter, keep Sigma.
+ * pose[B][7] = p(3) q(x,y,z,w), host. */
+int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose);
+
+/* ---- ensemble statistics (north_star: the only cross-GPU exchange) -------------------------------- */
+/* Writes [count, sum mu (DIM), sum mu mu^T lower-packed (DIM*(DIM+1)/2)] over this handle's filters into
+ * out (device or host pointer, 1 + DIM + DIM*(DIM+1)/2 doubles).  The caller all-reduces it (NCCL sum). */
+int uwvkf_ensemble_stats(uwvkf_handle h, double *out, int memspace);
+int64_t uwvkf_ensemble_stats_size(uwvkf_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWVKF_H */

@@ -23,7 +23,7 @@
 namespace orc {
 
 struct Policy {
-  double mean_tol = 1e-11;  // loop while |mean_delta| > mean_tol ...
+  double mean_tol = 1e-9;   // loop while |mean_delta| > mean_tol ...
   int mean_max_it = 100;    // ... and fewer than mean_max_it passes were made
 };
 

@@ -1,0 +1,152 @@
+// Device math shared by the uwvkf kernels: warp primitives, MTK manifold charts (SO3), the local
+// transverse-Mercator projection.  Formulas follow the reference's dependencies as frozen in
+// SURVEY.md Appendix C/D (MTK SO3 chart: q (+) d = q * exp(d), a (-) b = log(b^-1 a), series branch of
+// cos/sinc below eps^(1/4); pose_estimation::GeographicProjection = Krueger n-series TM on WGS-84).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uwvkf {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kMtkTol = 1e-11;      // MTK::tolerance<double>()
+constexpr double kEarthW = 7.292115e-5;  // pose_estimation::EARTHW
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+struct Quat {
+  double x, y, z, w;
+};
+struct Vec3 {
+  double x, y, z;
+};
+
+__device__ __forceinline__ Quat qmul(const Quat &a, const Quat &b) {
+  Quat o;
+  o.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  o.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  o.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  o.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  return o;
+}
+__device__ __forceinline__ Quat qconj(const Quat &a) { return Quat{-a.x, -a.y, -a.z, a.w}; }
+// q * v  (v + w t + u x t, t = 2 u x v)
+__device__ __forceinline__ Vec3 qrot(const Quat &q, const Vec3 &v) {
+  double tx = 2 * (q.y * v.z - q.z * v.y);
+  double ty = 2 * (q.z * v.x - q.x * v.z);
+  double tz = 2 * (q.x * v.y - q.y * v.x);
+  Vec3 o;
+  o.x = v.x + q.w * tx + (q.y * tz - q.z * ty);
+  o.y = v.y + q.w * ty + (q.z * tx - q.x * tz);
+  o.z = v.z + q.w * tz + (q.x * ty - q.y * tx);
+  return o;
+}
+__device__ __forceinline__ Vec3 qrot_inv(const Quat &q, const Vec3 &v) { return qrot(qconj(q), v); }
+__device__ __forceinline__ void qmat(const Quat &q, double R[9]) {
+  double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// MTK cos_sinc_sqrt: cos(sqrt(x2)), sin(sqrt(x2))/sqrt(x2)
+__device__ __forceinline__ void cos_sinc_sqrt(double x2, double &c, double &s) {
+  if (x2 >= 1.220703125e-4) {  // eps^(1/4) = 2^-13
+    double x = sqrt(x2), sn, cs;
+    sincos(x, &sn, &cs);
+    c = cs;
+    s = sn / x;
+  } else {
+    double cosi = 1., sinc = 1.;
+    double term = -0.5 * x2;
+    cosi += term; term *= (1 / 3.); sinc += term; term *= -(1 / 4.) * x2;
+    cosi += term; term *= (1 / 5.); sinc += term; term *= -(1 / 6.) * x2;
+    cosi += term; term *= (1 / 7.); sinc += term;
+    c = cosi;
+    s = sinc;
+  }
+}
+__device__ __forceinline__ Quat so3_exp(const Vec3 &v, double scale) {
+  double h = 0.5 * scale;
+  double n2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  double c, s;
+  cos_sinc_sqrt(h * h * n2, c, s);
+  double m = s * h;
+  return Quat{m * v.x, m * v.y, m * v.z, c};
+}
+__device__ __forceinline__ Vec3 so3_log(const Quat &q) {
+  double nv = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  if (nv < kMtkTol) nv = kMtkTol;
+  double s = 2.0 / nv * atan(nv / q.w);
+  return Vec3{s * q.x, s * q.y, s * q.z};
+}
+__device__ __forceinline__ Quat so3_boxplus(const Quat &q, const Vec3 &v, double scale) { return qmul(q, so3_exp(v, scale)); }
+__device__ __forceinline__ Vec3 so3_boxminus(const Quat &a, const Quat &b) { return so3_log(qmul(qconj(b), a)); }
+
+// ---- local transverse Mercator (Krueger series, order n^6); constants are filled on the host -----
+struct TMercConst {
+  double lat0, lon0, A, Ainv, xi0, e;
+  double alpha[6], beta[6], delta[6];
+};
+
+// NWU (x north, y west) -> geodetic latitude (the only output the process model consumes,
+// reference src/PoseUKF.cpp:29-30)
+__device__ __forceinline__ double tmerc_nav_to_lat(const TMercConst &tm, double x, double y) {
+  double xi = x * tm.Ainv + tm.xi0;
+  double eta = -y * tm.Ainv;
+  double s2, c2;
+  sincos(2 * xi, &s2, &c2);
+  double sh2 = sinh(2 * eta), ch2 = cosh(2 * eta);
+  // sin/cos(2j xi), sinh/cosh(2j eta) by angle addition
+  double sj = s2, cj = c2, shj = sh2, chj = ch2;
+  double xip = xi, etap = eta;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    xip -= tm.beta[j] * sj * chj;
+    etap -= tm.beta[j] * cj * shj;
+    double sn = sj * c2 + cj * s2, cn = cj * c2 - sj * s2;
+    double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
+    sj = sn; cj = cn; shj = shn; chj = chn;
+  }
+  double chi = asin(sin(xip) / cosh(etap));
+  double sc, cc;
+  sincos(2 * chi, &sc, &cc);
+  double sk = sc, ck = cc, phi = chi;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    phi += tm.delta[j] * sk;
+    double sn = sk * cc + ck * sc, cn = ck * cc - sk * sc;
+    sk = sn; ck = cn;
+  }
+  return phi;
+}
+
+// (lat, lon) -> NWU (x, y)   (reference src/PoseUKF.cpp:573 worldToNav)
+__device__ __forceinline__ void tmerc_world_to_nav(const TMercConst &tm, double lat, double lon, double &x, double &y) {
+  double tau = tan(lat);
+  double sig = sinh(tm.e * atanh(tm.e * tau / sqrt(1 + tau * tau)));
+  double taup = tau * sqrt(1 + sig * sig) - sig * sqrt(1 + tau * tau);
+  double dl = lon - tm.lon0;
+  double cdl = cos(dl);
+  double xip = atan2(taup, cdl);
+  double etap = asinh(sin(dl) / sqrt(taup * taup + cdl * cdl));
+  double xi = xip, eta = etap;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double a2 = 2.0 * (j + 1);
+    xi += tm.alpha[j] * sin(a2 * xip) * cosh(a2 * etap);
+    eta += tm.alpha[j] * cos(a2 * xip) * sinh(a2 * etap);
+  }
+  x = tm.A * (xi - tm.xi0);
+  y = -tm.A * eta;
+}
+
+}  // namespace uwvkf

@@ -1,0 +1,689 @@
+// PoseUKF engine: one warp per filter, filter block resident in shared memory, prefix-structured
+// unscented transform.
+//
+// What it computes is the ukfom recipe the reference drives (reference call
+// sites src/PoseUKF.cpp:462-465 predict, :476-611 updates): sigma points mu (+) (+-L.col(j)) with the
+// unscaled lower Cholesky factor, equal-weight iterated manifold mean, 1/2 sum d d^T covariances over all
+// 2n+1 points, S/K/gate/downdate, apply_delta re-draw.  HOW it computes it: because L is lower
+// triangular and the tangent order is fixed, a model that reads only the first k tangent coordinates
+// sees identical sigma points for all columns j >= k, so those 2(n-k) points are carried as a multiplicity
+// of the centre point and every covariance block becomes an O(n^2) expression in Sigma and the k x k
+// leading Cholesky factor.  tests/test_structured_equivalence.py proves the identity on the CPU.
+#pragma once
+#include "dmath.cuh"
+
+namespace uwvkf {
+namespace pose {
+
+constexpr int N = 53;        // tangent DOF
+constexpr int DIM = 54;      // stored doubles of mu
+constexpr int NP = 1431;     // packed lower triangle
+constexpr int BLK = 1488;    // doubles per filter block in HBM: [mu 54 | pad 2 | Sigma packed 1431 | pad 1]
+constexpr int OFF_MU = 0;
+constexpr int OFF_S = 56;
+constexpr int NOFF = 28;     // Markov offsets per filter
+
+// stored indices of mu
+enum { P_POS = 0, P_ORI = 3, P_VEL = 7, P_ACC = 10, P_BG = 13, P_BA = 16, P_G = 19, P_INERTIA = 20, P_LIN = 29,
+       P_QUAD = 38, P_WV = 47, P_WVB = 49, P_BADCP = 51, P_RHO = 53 };
+// tangent indices
+enum { T_POS = 0, T_ORI = 3, T_VEL = 6, T_ACC = 9, T_BG = 12, T_BA = 15, T_G = 18, T_INERTIA = 19, T_LIN = 28,
+       T_QUAD = 37, T_WV = 46, T_WVB = 48, T_BADCP = 50, T_RHO = 52 };
+
+enum { ST_NOT_SPD = 1u, ST_NAN_MEAS = 2u, ST_GATE_REJECTED = 4u, ST_MEAN_NOT_CONVERGED = 8u };
+
+enum MeasKind { M_XY = 0, M_Z = 1, M_PRESSURE = 2, M_ACCELERATION = 3, M_VELOCITY = 4, M_WATER_VELOCITY = 5,
+                M_GEOGRAPHIC = 6, M_DELAYED_XY = 7 };
+
+struct Params {
+  TMercConst tm;
+  double gyro_bias_tau, gyro_bias_offset[3];
+  double acc_bias_tau, acc_bias_offset[3];
+  double inertia_tau, lin_damping_tau, quad_damping_tau;
+  double wv_tau, wv_limits, wv_scale, adcp_bias_tau, atm_pressure, rho_tau;
+  double imu_in_body[3];
+  double mean_tol;
+  int mean_max_it;
+};
+
+struct Op {
+  int type;            // 0 = predict, 1 = update
+  int kind;            // MeasKind for updates
+  double dt;           // predict
+  const double *z;     // device [B][m]
+  const double *Rdev;  // device [B][m*m] or nullptr -> R below
+  const uint8_t *valid;  // device [B] or nullptr
+  double R[9];
+  double aux[4];
+};
+
+struct Launch {
+  double *state;           // [B][BLK]
+  const double *offsets;   // [B][NOFF]
+  const double *rot_rate;  // [B][3]
+  uint32_t *status;        // [B]
+  const double *Q;         // packed lower, column-major, NP doubles
+  long long B;
+  int nops;
+  Op ops[3];
+};
+
+// Sigma is stored as the lower triangle packed by columns: column j holds rows j..N-1.
+// The first k columns (the "panel" every prefix-k model needs) are therefore a prefix of the array.
+__host__ __device__ __forceinline__ int cidx(int i, int j) { return j * N - ((j * (j - 1)) >> 1) + (i - j); }
+template <int K>
+__device__ __forceinline__ int lidx(int i, int j) { return j * K - ((j * (j - 1)) >> 1) + (i - j); }
+__device__ __forceinline__ int sidx(int a, int b) { return a >= b ? cidx(a, b) : cidx(b, a); }
+
+// per-warp shared-memory layout (doubles)
+template <int KMAX>
+struct WL {
+  static constexpr int MG = 3;                                      // rows of G / T / KS (max measurement dim)
+  static constexpr int LSZ = ((KMAX * (KMAX + 1) / 2 + 1) / 2) * 2;
+  static constexpr int KE = ((KMAX + 1) / 2) * 2;
+  static constexpr int L = BLK;             // leading-block Cholesky factor, packed by columns (dimension K)
+  static constexpr int INVD = L + LSZ;      // 1 / L_jj
+  static constexpr int G = INVD + KE;       // MG x KE : A (or B) then G = A L^-1
+  static constexpr int T = G + MG * KE;     // MG x 56 : G Sigma[0:k,:]  (= Pxz^T, then K^T)
+  static constexpr int KS = T + MG * 56;    // MG x 56 : (K S)^T
+  static constexpr int DL = KS + MG * 56;   // 56 : delta = K nu
+  static constexpr int F = DL + 56;         // 56 : diagonal of the affine process map
+  static constexpr int TOTAL = F + 56;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Cholesky of the leading K x K block of Sigma.  K <= 32: lane i owns row i in registers, pivots and
+// column entries travel by shuffles (no shared-memory round trips inside the recurrence).
+template <int K>
+__device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double *invd, int lane) {
+  if constexpr (K <= 32) {
+    double a[K];
+    const int i = lane;
+#pragma unroll
+    for (int c = 0; c < K; ++c) a[c] = (i < K && c <= i) ? S[cidx(i, c)] : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      double d = bcast(a[j], j);
+      ok = ok && (d > 0.0);
+      double inv = rsqrt(d);
+      a[j] = (i == j) ? d * inv : a[j] * inv;
+      if (i == j) invd[j] = inv;
+#pragma unroll
+      for (int c = j + 1; c < K; ++c) {
+        double lcj = bcast(a[j], c);
+        a[c] = fma(-a[j], lcj, a[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+      if (i < K && c <= i) Lw[lidx<K>(i, c)] = a[c];
+    __syncwarp();
+    return ok;
+  } else {
+    // general path (K up to N): right-looking factorisation in shared memory
+    constexpr int LP = K * (K + 1) / 2;
+    for (int j = 0; j < K; ++j)
+      for (int i = j + lane; i < K; i += 32) Lw[lidx<K>(i, j)] = S[cidx(i, j)];
+    (void)LP;
+    __syncwarp();
+    bool ok = true;
+    for (int j = 0; j < K; ++j) {
+      double d = Lw[lidx<K>(j, j)];
+      ok = ok && (d > 0.0);
+      double inv = rsqrt(d);
+      __syncwarp();
+      for (int i = j + 1 + lane; i < K; i += 32) Lw[lidx<K>(i, j)] *= inv;
+      if (lane == 0) { Lw[lidx<K>(j, j)] = d * inv; invd[j] = inv; }
+      __syncwarp();
+      for (int c = j + 1; c < K; ++c) {
+        double lcj = Lw[lidx<K>(c, j)];
+        for (int i = c + lane; i < K; i += 32) Lw[lidx<K>(i, c)] = fma(-Lw[lidx<K>(i, j)], lcj, Lw[lidx<K>(i, c)]);
+      }
+      __syncwarp();
+    }
+    return ok;
+  }
+}
+
+// G <- G L^-1 for the K x K lower factor L (G is M x K, row stride gs).
+template <int K, int M>
+__device__ __forceinline__ void solve_right(double *G, int gs, const double *Lw, const double *invd, int lane) {
+  if constexpr (K <= 32) {
+    double acc[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) acc[r] = (lane < K) ? G[r * gs + lane] : 0.0;
+    for (int c = K - 1; c >= 0; --c) {
+      double ic = invd[c];
+      double g[M];
+#pragma unroll
+      for (int r = 0; r < M; ++r) g[r] = bcast(acc[r] * ic, c);
+      if (lane < c) {
+        double l = Lw[lidx<K>(c, lane)];
+#pragma unroll
+        for (int r = 0; r < M; ++r) acc[r] = fma(-g[r], l, acc[r]);
+      } else if (lane == c) {
+#pragma unroll
+        for (int r = 0; r < M; ++r) acc[r] = g[r];
+      }
+    }
+    if (lane < K) {
+#pragma unroll
+      for (int r = 0; r < M; ++r) G[r * gs + lane] = acc[r];
+    }
+    __syncwarp();
+  } else {
+    for (int c = K - 1; c >= 0; --c) {
+      double ic = invd[c];
+      double g[M];
+#pragma unroll
+      for (int r = 0; r < M; ++r) g[r] = G[r * gs + c] * ic;
+      __syncwarp();
+      for (int j = lane; j < c; j += 32) {
+        double l = Lw[lidx<K>(c, j)];
+#pragma unroll
+        for (int r = 0; r < M; ++r) G[r * gs + j] = fma(-g[r], l, G[r * gs + j]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < M; ++r) G[r * gs + c] = g[r];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// T[r][x] = sum_{b<K} G[r][b] * Sigma[b][x]   for x = 0..N-1
+template <int K, int M>
+__device__ __forceinline__ void g_times_sigma(const double *G, int gs, const double *S, double *T, int lane) {
+  for (int x = lane; x < N; x += 32) {
+    double acc[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) acc[r] = 0.0;
+#pragma unroll 4
+    for (int b = 0; b < K; ++b) {
+      double s = S[sidx(b, x)];
+#pragma unroll
+      for (int r = 0; r < M; ++r) acc[r] = fma(G[r * gs + b], s, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < M; ++r) T[r * 56 + x] = acc[r];
+  }
+  __syncwarp();
+}
+
+// equal-weight iterated SO3 mean over 2N+1 logical points; each lane holds ROUNDS points with
+// multiplicities wt (ukfom mean_sigma_points restricted to the one non-vector component).
+template <int ROUNDS>
+__device__ __forceinline__ Quat so3_mean(const Quat (&qp)[ROUNDS], const double (&wt)[ROUNDS], double tol, int max_it,
+                                         unsigned &status) {
+  Quat r{bcast(qp[0].x, 0), bcast(qp[0].y, 0), bcast(qp[0].z, 0), bcast(qp[0].w, 0)};
+  int it = 0;
+  double nrm;
+  do {
+    double mx = 0, my = 0, mz = 0;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+      Vec3 d = so3_boxminus(qp[k], r);
+      mx = fma(wt[k], d.x, mx); my = fma(wt[k], d.y, my); mz = fma(wt[k], d.z, mz);
+    }
+    mx = warp_sum(mx) / double(2 * N + 1);
+    my = warp_sum(my) / double(2 * N + 1);
+    mz = warp_sum(mz) / double(2 * N + 1);
+    r = so3_boxplus(r, Vec3{mx, my, mz}, 1.0);
+    nrm = sqrt(mx * mx + my * my + mz * mz);
+  } while (nrm > tol && ++it < max_it);
+  if (it >= max_it) status |= ST_MEAN_NOT_CONVERGED;
+  return r;
+}
+
+// Unscented transform of the orientation rows with the leading-K sigma points qp (one round, K <= 15):
+// returns the new mean quaternion, writes Sigma_oo (6 values) and T = (A L^-1) Sigma[0:K,:] (3 x N).
+template <int K, int KMAX>
+__device__ __forceinline__ Quat ori_transform(double *w, const Quat &qp, int p, const Params &P, double soo[6], int lane,
+                                              unsigned &status) {
+  using W = WL<KMAX>;
+  double *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *G = w + W::G, *T = w + W::T;
+  const bool act = p < 2 * K + 1;
+  const bool on = act && p > 0;
+  const int j = (p - 1) >> 1;
+  Quat qa[1] = {qp};
+  double wa[1] = {p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0)};
+  Quat r = so3_mean<1>(qa, wa, P.mean_tol, P.mean_max_it, status);
+  Vec3 a = so3_boxminus(qp, r);
+  const double hw = 0.5 * wa[0];
+  soo[0] = warp_sum(hw * a.x * a.x);
+  soo[1] = warp_sum(hw * a.y * a.x);
+  soo[2] = warp_sum(hw * a.z * a.x);
+  soo[3] = warp_sum(hw * a.y * a.y);
+  soo[4] = warp_sum(hw * a.z * a.y);
+  soo[5] = warp_sum(hw * a.z * a.z);
+  // A_j = 1/2 (a_{2j+1} - a_{2j+2}): odd lanes pair with lane + 1
+  double nx = __shfl_down_sync(kFull, a.x, 1), ny = __shfl_down_sync(kFull, a.y, 1), nz = __shfl_down_sync(kFull, a.z, 1);
+  if (on && (p & 1)) {
+    G[0 * W::KE + j] = 0.5 * (a.x - nx);
+    G[1 * W::KE + j] = 0.5 * (a.y - ny);
+    G[2 * W::KE + j] = 0.5 * (a.z - nz);
+  }
+  __syncwarp();
+  solve_right<K, 3>(G, W::KE, Lw, invd, lane);
+  g_times_sigma<K, 3>(G, W::KE, S, T, lane);
+  return r;
+}
+
+// In-place congruence Sigma <- C Sigma C^T with C = I + dt * E(dst <- src) on 3 consecutive rows.
+__device__ __forceinline__ void couple3(double *S, int d0, int s0, double dt, int lane) {
+  double nb = 0.0;
+  int bi = 0, bj = 0;
+  if (lane < 6) {
+    bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+    bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+    nb = S[sidx(d0 + bi, d0 + bj)] + dt * (S[sidx(s0 + bi, d0 + bj)] + S[sidx(d0 + bi, s0 + bj)]) +
+         dt * dt * S[sidx(s0 + bi, s0 + bj)];
+  }
+  __syncwarp();
+  for (int b = lane; b < N; b += 32) {
+    if (b < d0 || b >= d0 + 3) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) S[sidx(d0 + i, b)] += dt * S[sidx(s0 + i, b)];
+    }
+  }
+  __syncwarp();
+  if (lane < 6) S[cidx(d0 + bi, d0 + bj)] = nb;
+  __syncwarp();
+}
+
+// diagonal of the affine part of the process model (reference src/PoseUKF.cpp:37-78)
+__device__ __forceinline__ double affine_factor(int t, const Params &P, double dt) {
+  if (t < T_BG) return 1.0;
+  if (t < T_BA) return 1.0 - dt / P.gyro_bias_tau;
+  if (t < T_G) return 1.0 - dt / P.acc_bias_tau;
+  if (t < T_INERTIA) return 1.0;
+  if (t < T_LIN) return 1.0 - dt / P.inertia_tau;
+  if (t < T_QUAD) return 1.0 - dt / P.lin_damping_tau;
+  if (t < T_WV) return 1.0 - dt / P.quad_damping_tau;
+  if (t < T_BADCP) return 1.0 - dt / P.wv_tau;
+  if (t < T_RHO) return 1.0 - dt / P.adcp_bias_tau;
+  return 1.0 - dt / P.rho_tau;
+}
+
+// new value of stored component s (not orientation) under the process model, src/PoseUKF.cpp:25-78
+__device__ __forceinline__ double affine_mean(int s, const double *mu, const double *off, const Params &P, double dt) {
+  double x = mu[s];
+  if (s < P_ORI) return x + dt * mu[P_VEL + s];
+  if (s < P_ACC) return x + dt * mu[s + 3];   // velocity += acceleration * dt
+  if (s < P_BG) return x;
+  if (s < P_BA) return x + dt * ((-1.0 / P.gyro_bias_tau) * (x - P.gyro_bias_offset[s - P_BG]));
+  if (s < P_G) return x + dt * ((-1.0 / P.acc_bias_tau) * (x - P.acc_bias_offset[s - P_BA]));
+  if (s < P_INERTIA) return x;
+  if (s < P_LIN) return x + dt * ((-1.0 / P.inertia_tau) * (x - off[s - P_INERTIA]));
+  if (s < P_QUAD) return x + dt * ((-1.0 / P.lin_damping_tau) * (x - off[9 + s - P_LIN]));
+  if (s < P_WV) return x + dt * ((-1.0 / P.quad_damping_tau) * (x - off[18 + s - P_QUAD]));
+  if (s < P_BADCP) return x + dt * ((-1.0 / P.wv_tau) * x);
+  if (s < P_RHO) return x + dt * ((-1.0 / P.adcp_bias_tau) * x);
+  return x + dt * ((-1.0 / P.rho_tau) * (x - off[27]));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// predictionStepImpl (reference src/PoseUKF.cpp:446-466) with processModel (src/PoseUKF.cpp:12-84).
+// The orientation is the only non-affine output and reads (p, q, b_gyro) = tangent prefix 15.
+template <int KMAX>
+__device__ __forceinline__ bool predict(double *w, const double *Qs, const uint16_t *lut, const double *off,
+                                        const double *wm_g, const Params &P, double dt, int lane, unsigned &status) {
+  using W = WL<KMAX>;
+  constexpr int K = 15;
+  double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *T = w + W::T, *fv = w + W::F;
+  if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
+  const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
+  const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};
+  const Vec3 wm{wm_g[0], wm_g[1], wm_g[2]};
+  const int p = lane;
+  const bool on = p > 0 && p < 2 * K + 1;
+  const int j = (p - 1) >> 1;
+  const double sg = (p & 1) ? 1.0 : -1.0;
+  auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+  Quat qp;
+  {
+    double px = mu[P_POS] + d(0), py = mu[P_POS + 1] + d(1);
+    Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
+    Vec3 wb{wm.x - (mu[P_BG] + d(12)), wm.y - (mu[P_BG + 1] + d(13)), wm.z - (mu[P_BG + 2] + d(14))};
+    double lat = tmerc_nav_to_lat(P.tm, px, py);
+    double sl, cl;
+    sincos(lat, &sl, &cl);
+    Vec3 wn = qrot(qq, wb);
+    wn.x -= kEarthW * cl;
+    wn.z -= kEarthW * sl;
+    qp = so3_boxplus(qq, wn, dt);
+  }
+  double soo[6];
+  Quat r = ori_transform<K, KMAX>(w, qp, p, P, soo, lane, status);
+
+  // effective process noise pieces (src/PoseUKF.cpp:448-460)
+  const double dt2 = dt * dt;
+  double qoo[6];
+  {
+    double Rm[9], Qo[9], t[9];
+    qmat(q, Rm);
+    Qo[0] = Qs[cidx(3, 3)]; Qo[1] = Qs[cidx(4, 3)]; Qo[2] = Qs[cidx(5, 3)];
+    Qo[3] = Qo[1];          Qo[4] = Qs[cidx(4, 4)]; Qo[5] = Qs[cidx(5, 4)];
+    Qo[6] = Qo[2];          Qo[7] = Qo[5];          Qo[8] = Qs[cidx(5, 5)];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) t[a * 3 + b] = Rm[a * 3] * Qo[b] + Rm[a * 3 + 1] * Qo[3 + b] + Rm[a * 3 + 2] * Qo[6 + b];
+    // (i, j) order matches soo: (0,0) (1,0) (2,0) (1,1) (2,1) (2,2)
+    auto rq = [&](int a, int b) { return t[a * 3] * Rm[b * 3] + t[a * 3 + 1] * Rm[b * 3 + 1] + t[a * 3 + 2] * Rm[b * 3 + 2]; };
+    qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
+  }
+  const double add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
+
+  // affine map: diagonal factors and new mean (registers until Sigma is done)
+  for (int t = lane; t < N; t += 32) fv[t] = affine_factor(t, P, dt);
+  double nm0 = 0, nm1 = 0;
+  {
+    int s0 = lane, s1 = lane + 32;
+    if (s0 < P_ORI || s0 >= P_VEL) nm0 = affine_mean(s0, mu, off, P, dt);
+    if (s1 < DIM) nm1 = affine_mean(s1, mu, off, P, dt);
+  }
+  __syncwarp();
+  // Sigma <- F Sigma F^T on the affine rows: couplings p <- v, then v <- a, then the diagonal scaling + Q
+  couple3(S, T_POS, T_VEL, dt, lane);
+  couple3(S, T_VEL, T_ACC, dt, lane);
+  for (int e = lane; e < NP; e += 32) {
+    unsigned ij = lut[e];
+    int i = ij & 0xff, jj = ij >> 8;
+    if ((i >= 3 && i < 6) || (jj >= 3 && jj < 6)) continue;
+    double v = fv[i] * fv[jj] * S[e] + dt2 * Qs[e];
+    if (i == jj && i >= T_WV && i < T_BADCP) v += dt2 * add;
+    S[e] = v;
+  }
+  // orientation rows: T F^T  (+ Q cross terms, zero in the reference's configuration but part of the API)
+  for (int x = lane; x < N; x += 32) {
+    if (x >= 3 && x < 6) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double tp = fv[x] * T[c * 56 + x];
+      if (x < 3) tp += dt * T[c * 56 + x + 6];
+      else if (x >= T_VEL && x < T_ACC) tp += dt * T[c * 56 + x + 3];
+      int e = sidx(3 + c, x);
+      S[e] = tp + dt2 * Qs[e];
+    }
+  }
+  if (lane < 6) {
+    int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+    int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+    S[cidx(3 + bi, 3 + bj)] = soo[lane] + dt2 * qoo[lane];
+  }
+  // mean
+  {
+    int s0 = lane, s1 = lane + 32;
+    if (s0 < P_ORI || s0 >= P_VEL) mu[s0] = nm0;
+    if (s1 < DIM) mu[s1] = nm1;
+    if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
+  }
+  __syncwarp();
+  return true;
+}
+
+// ukfom apply_delta(delta): only the orientation (tangent 3..5, prefix 6) is a non-vector component.
+template <int KMAX>
+__device__ __forceinline__ bool apply_delta(double *w, const Params &P, int lane, unsigned &status) {
+  using W = WL<KMAX>;
+  constexpr int K = 6;
+  double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *T = w + W::T, *dl = w + W::DL;
+  if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
+  const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
+  const int p = lane;
+  const bool on = p > 0 && p < 2 * K + 1;
+  const int j = (p - 1) >> 1;
+  const double sg = (p & 1) ? 1.0 : -1.0;
+  auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+  Quat qp = so3_boxplus(q, Vec3{dl[3] + d(3), dl[4] + d(4), dl[5] + d(5)}, 1.0);
+  double soo[6];
+  Quat r = ori_transform<K, KMAX>(w, qp, p, P, soo, lane, status);
+  for (int x = lane; x < N; x += 32) {
+    if (x >= 3 && x < 6) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) S[sidx(3 + c, x)] = T[c * 56 + x];
+  }
+  if (lane < 6) {
+    int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+    int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+    S[cidx(3 + bi, 3 + bj)] = soo[lane];
+  }
+  for (int s = lane; s < DIM; s += 32) {
+    if (s < P_ORI) mu[s] += dl[s];
+    else if (s >= P_VEL) mu[s] += dl[s - 1];
+  }
+  if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
+  __syncwarp();
+  return true;
+}
+
+// ---- measurement models (reference src/PoseUKF.cpp:87-151): K = tangent prefix read, M = dimension ----
+template <int KIND> struct Meas;
+template <> struct Meas<M_XY> {   // src/PoseUKF.cpp:87-92
+  static constexpr int K = 2, M = 2;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+    o[0] = mu[P_POS] + d(0); o[1] = mu[P_POS + 1] + d(1);
+  }
+};
+template <> struct Meas<M_Z> {    // src/PoseUKF.cpp:100-105
+  static constexpr int K = 3, M = 1;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+    o[0] = mu[P_POS + 2] + d(2);
+  }
+};
+template <> struct Meas<M_VELOCITY> {   // src/PoseUKF.cpp:117-123
+  static constexpr int K = 9, M = 3;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+    Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
+    Vec3 v = qrot_inv(q, Vec3{mu[P_VEL] + d(6), mu[P_VEL + 1] + d(7), mu[P_VEL + 2] + d(8)});
+    o[0] = v.x; o[1] = v.y; o[2] = v.z;
+  }
+};
+template <> struct Meas<M_ACCELERATION> {   // src/PoseUKF.cpp:125-131
+  static constexpr int K = 19, M = 3;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+    Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
+    Vec3 a{mu[P_ACC] + d(9), mu[P_ACC + 1] + d(10), (mu[P_ACC + 2] + d(11)) + (mu[P_G] + d(18))};
+    Vec3 v = qrot_inv(q, a);
+    o[0] = v.x + (mu[P_BA] + d(15)); o[1] = v.y + (mu[P_BA + 1] + d(16)); o[2] = v.z + (mu[P_BA + 2] + d(17));
+  }
+};
+template <> struct Meas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115 ; aux = pressure_sensor_in_imu
+  static constexpr int K = 53, M = 1;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+    Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
+    Vec3 rn = qrot(q, Vec3{aux[0], aux[1], aux[2]});
+    double zn = (mu[P_POS + 2] + d(2)) + rn.z;
+    o[0] = P.atm_pressure - zn * (mu[P_G] + d(18)) * (mu[P_RHO] + d(52));
+  }
+};
+template <> struct Meas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151 ; aux[0] = cell_weighting
+  static constexpr int K = 52, M = 2;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &, double *o) {
+    Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
+    double vx = mu[P_VEL] + d(6), vy = mu[P_VEL + 1] + d(7), vz = mu[P_VEL + 2] + d(8);
+    Vec3 b = qrot_inv(q, Vec3{vx - (mu[P_WVB] + d(48)), vy - (mu[P_WVB + 1] + d(49)), vz - 0.0});
+    Vec3 a = qrot_inv(q, Vec3{vx - (mu[P_WV] + d(46)), vy - (mu[P_WV + 1] + d(47)), vz - 0.0});
+    double wgt = aux[0];
+    o[0] = wgt * b.x + (1 - wgt) * a.x + (mu[P_BADCP] + d(50));
+    o[1] = wgt * b.y + (1 - wgt) * a.y + (mu[P_BADCP + 1] + d(51));
+  }
+};
+
+template <int M>
+__device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
+  if constexpr (M == 1) {
+    Si[0] = 1.0 / S[0];
+  } else if constexpr (M == 2) {
+    double id = 1.0 / (S[0] * S[3] - S[1] * S[2]);
+    Si[0] = S[3] * id; Si[1] = -S[1] * id; Si[2] = -S[2] * id; Si[3] = S[0] * id;
+  } else {
+    double c00 = S[4] * S[8] - S[5] * S[7], c01 = S[5] * S[6] - S[3] * S[8], c02 = S[3] * S[7] - S[4] * S[6];
+    double id = 1.0 / (S[0] * c00 + S[1] * c01 + S[2] * c02);
+    Si[0] = c00 * id; Si[1] = (S[2] * S[7] - S[1] * S[8]) * id; Si[2] = (S[1] * S[5] - S[2] * S[4]) * id;
+    Si[3] = c01 * id; Si[4] = (S[0] * S[8] - S[2] * S[6]) * id; Si[5] = (S[2] * S[3] - S[0] * S[5]) * id;
+    Si[6] = c02 * id; Si[7] = (S[1] * S[6] - S[0] * S[7]) * id; Si[8] = (S[0] * S[4] - S[1] * S[3]) * id;
+  }
+}
+
+// ukfom update(z, h, R, gate) for a vector measurement (reference call sites src/PoseUKF.cpp:479-610).
+// gate95: the reference's d2p95 (src/PoseUKF.cpp:275-286), otherwise accept_any.
+template <int KIND, int KMAX>
+__device__ __forceinline__ bool update(double *w, const uint16_t *lut, const double *z, const double *Rm, const double *aux,
+                                       bool gate95, const Params &P, int lane, unsigned &status) {
+  using W = WL<KMAX>;
+  using MM = Meas<KIND>;
+  constexpr int K = MM::K, M = MM::M;
+  static_assert(K <= KMAX, "kernel instantiated with too small a panel");
+  constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
+  double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *G = w + W::G, *T = w + W::T,
+         *KS = w + W::KS, *dl = w + W::DL;
+  if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
+  // sigma points through the measurement model
+  double Z[ROUNDS][M], wt[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int p = lane + 32 * r;
+    const bool act = p < NPTS;
+    const bool on = act && p > 0;
+    const int j = (p - 1) >> 1;
+    const double sg = (p & 1) ? 1.0 : -1.0;
+    auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+    MM::eval(mu, d, aux, P, Z[r]);
+    wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
+  }
+  // mean (ukfom mean_sigma_points on a vector manifold)
+  double zb[M];
+#pragma unroll
+  for (int a = 0; a < M; ++a) zb[a] = bcast(Z[0][a], 0);
+  {
+    int it = 0;
+    double nrm;
+    do {
+      nrm = 0;
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double m = 0;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) m = fma(wt[r], Z[r][a] - zb[a], m);
+        m = warp_sum(m) / double(2 * N + 1);
+        zb[a] += m;
+        nrm += m * m;
+      }
+      nrm = sqrt(nrm);
+    } while (nrm > P.mean_tol && ++it < P.mean_max_it);
+    if (it >= P.mean_max_it) status |= ST_MEAN_NOT_CONVERGED;
+  }
+  // S = 1/2 sum dz dz^T + R
+  double Szz[M * M];
+#pragma unroll
+  for (int a = 0; a < M; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      double s = 0;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) s = fma(0.5 * wt[r] * (Z[r][a] - zb[a]), Z[r][b] - zb[b], s);
+      s = warp_sum(s);
+      Szz[a * M + b] = s + Rm[a * M + b];
+      Szz[b * M + a] = s + Rm[b * M + a];
+    }
+  // B_j = 1/2 (Z_{2j+1} - Z_{2j+2}) -> G, then G <- B L^-1, T = G Sigma[0:K,:] = Pxz^T
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int p = lane + 32 * r;
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double src = Z[r][a];
+      if (r + 1 < ROUNDS) { if (lane == 0) src = Z[r + 1 < ROUNDS ? r + 1 : r][a]; }
+      double nxt = __shfl_sync(kFull, src, (lane + 1) & 31);
+      if ((p & 1) && p < NPTS) G[a * W::KE + ((p - 1) >> 1)] = 0.5 * (Z[r][a] - nxt);
+    }
+  }
+  __syncwarp();
+  solve_right<K, M>(G, W::KE, Lw, invd, lane);
+  g_times_sigma<K, M>(G, W::KE, S, T, lane);
+  // gain, innovation, gate
+  double Si[M * M];
+  sym_inverse<M>(Szz, Si);
+  double nu[M];
+#pragma unroll
+  for (int a = 0; a < M; ++a) nu[a] = z[a] - zb[a];
+  double d2 = 0;
+#pragma unroll
+  for (int a = 0; a < M; ++a)
+#pragma unroll
+    for (int b = 0; b < M; ++b) d2 += nu[a] * Si[a * M + b] * nu[b];
+  if (gate95 && d2 > 5.991) { status |= ST_GATE_REJECTED; return false; }
+  for (int x = lane; x < N; x += 32) {
+    double pxz[M], kx[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) pxz[a] = T[a * 56 + x];
+    double dx = 0;
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < M; ++c) s += pxz[c] * Si[c * M + a];
+      kx[a] = s;
+      dx += s * nu[a];
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < M; ++c) s += kx[c] * Szz[c * M + a];
+      KS[a * 56 + x] = s;
+      T[a * 56 + x] = kx[a];
+    }
+    dl[x] = dx;
+  }
+  __syncwarp();
+  // Sigma -= (K S) K^T
+  for (int e = lane; e < NP; e += 32) {
+    unsigned ij = lut[e];
+    int i = ij & 0xff, jj = ij >> 8;
+    double s = S[e];
+#pragma unroll
+    for (int c = 0; c < M; ++c) s = fma(-KS[c * 56 + i], T[c * 56 + jj], s);
+    S[e] = s;
+  }
+  __syncwarp();
+  // T is overwritten by apply_delta; keep K in registers for a possible rollback
+  double kr[2][M], ksr[2][M];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int x = lane + 32 * h;
+#pragma unroll
+    for (int a = 0; a < M; ++a) { kr[h][a] = x < N ? T[a * 56 + x] : 0.0; ksr[h][a] = x < N ? KS[a * 56 + x] : 0.0; }
+  }
+  __syncwarp();
+  if (!apply_delta<KMAX>(w, P, lane, status)) {
+    // downdated Sigma lost definiteness in its leading block: roll the downdate back, leave the filter as it was
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int x = lane + 32 * h;
+      if (x < N) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) { T[a * 56 + x] = kr[h][a]; KS[a * 56 + x] = ksr[h][a]; }
+      }
+    }
+    __syncwarp();
+    for (int e = lane; e < NP; e += 32) {
+      unsigned ij = lut[e];
+      int i = ij & 0xff, jj = ij >> 8;
+      double s = S[e];
+#pragma unroll
+      for (int c = 0; c < M; ++c) s = fma(KS[c * 56 + i], T[c * 56 + jj], s);
+      S[e] = s;
+    }
+    __syncwarp();
+    return false;
+  }
+  return true;
+}
+
+}  // namespace pose
+}  // namespace uwvkf

@@ -1,0 +1,643 @@
+// uwvkf C ABI (include/uwvkf.h) + kernel launchers.  Thin host code over the CUDA kernels; no CPU path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/uwvkf.h"
+#include "pose_engine.cuh"
+
+namespace {
+
+using namespace uwvkf;
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(UWVKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+__device__ uint16_t g_lut[pose::NP];  // packed index -> (row | col << 8)
+
+// ------------------------------------------------------------------------------------------------------
+// PoseUKF step kernel: one warp per filter, persistent CTAs, filter block staged in shared memory.
+template <int KMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a, const __grid_constant__ pose::Params P) {
+  using W = pose::WL<KMAX>;
+  extern __shared__ __align__(16) double smem[];
+  double *Qs = smem;
+  uint16_t *lut = reinterpret_cast<uint16_t *>(smem + 1432);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w = smem + 1432 + 360 + warp * W::TOTAL;
+  for (int e = threadIdx.x; e < pose::NP; e += blockDim.x) {
+    Qs[e] = a.Q[e];
+    lut[e] = g_lut[e];
+  }
+  __syncthreads();
+  for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
+    {
+      const double2 *src = reinterpret_cast<const double2 *>(a.state + f * pose::BLK);
+      double2 *dst = reinterpret_cast<double2 *>(w);
+#pragma unroll 4
+      for (int k = lane; k < pose::BLK / 2; k += 32) dst[k] = __ldcs(src + k);
+    }
+    __syncwarp();
+    unsigned st = 0;
+    bool dirty = false;
+    for (int o = 0; o < a.nops; ++o) {
+      const pose::Op &op = a.ops[o];
+      if (op.type == 0) {
+        dirty |= pose::predict<KMAX>(w, Qs, lut, a.offsets + f * pose::NOFF, a.rot_rate + f * 3, P, op.dt, lane, st);
+        continue;
+      }
+      if (op.valid && !op.valid[f]) continue;
+      const int kind = op.kind;
+      const int m = (kind == pose::M_Z || kind == pose::M_PRESSURE) ? 1 : ((kind == pose::M_VELOCITY || kind == pose::M_ACCELERATION) ? 3 : 2);
+      double z[3], R[9];
+      bool bad = false;
+      for (int k = 0; k < m; ++k) { z[k] = op.z[f * m + k]; bad |= isnan(z[k]); }
+      for (int k = 0; k < m * m; ++k) { R[k] = op.Rdev ? op.Rdev[f * m * m + k] : op.R[k]; bad |= isnan(R[k]); }
+      if (bad) { st |= pose::ST_NAN_MEAS; continue; }
+      switch (kind) {
+        case pose::M_XY: dirty |= pose::update<pose::M_XY, KMAX>(w, lut, z, R, op.aux, false, P, lane, st); break;
+        case pose::M_Z: dirty |= pose::update<pose::M_Z, KMAX>(w, lut, z, R, op.aux, false, P, lane, st); break;
+        case pose::M_VELOCITY: dirty |= pose::update<pose::M_VELOCITY, KMAX>(w, lut, z, R, op.aux, false, P, lane, st); break;
+        case pose::M_ACCELERATION: dirty |= pose::update<pose::M_ACCELERATION, KMAX>(w, lut, z, R, op.aux, false, P, lane, st); break;
+        case pose::M_GEOGRAPHIC: {  // reference src/PoseUKF.cpp:572-578
+          double px, py;
+          tmerc_world_to_nav(P.tm, z[0], z[1], px, py);
+          Vec3 lever = qrot(Quat{w[3], w[4], w[5], w[6]}, Vec3{op.aux[0], op.aux[1], op.aux[2]});
+          z[0] = px - lever.x; z[1] = py - lever.y;
+          dirty |= pose::update<pose::M_XY, KMAX>(w, lut, z, R, op.aux, true, P, lane, st);
+          break;
+        }
+        case pose::M_DELAYED_XY: {  // reference src/PoseUKF.cpp:516-521
+          z[0] = z[0] + (w[0] - op.aux[0]); z[1] = z[1] + (w[1] - op.aux[1]);
+          dirty |= pose::update<pose::M_XY, KMAX>(w, lut, z, R, op.aux, false, P, lane, st);
+          break;
+        }
+        default:
+          if constexpr (KMAX >= 53) {
+            if (kind == pose::M_PRESSURE) dirty |= pose::update<pose::M_PRESSURE, KMAX>(w, lut, z, R, op.aux, false, P, lane, st);
+            else if (kind == pose::M_WATER_VELOCITY) dirty |= pose::update<pose::M_WATER_VELOCITY, KMAX>(w, lut, z, R, op.aux, true, P, lane, st);
+          }
+          break;
+      }
+    }
+    __syncwarp();
+    if (dirty) {
+      double2 *dst = reinterpret_cast<double2 *>(a.state + f * pose::BLK);
+      const double2 *src = reinterpret_cast<const double2 *>(w);
+#pragma unroll 4
+      for (int k = lane; k < pose::BLK / 2; k += 32) __stcs(dst + k, src[k]);
+    }
+    if (st && lane == 0) a.status[f] |= st;
+    __syncwarp();
+  }
+}
+
+// host (mu[count][54], cov[count][53*53] or one shared cov) -> device blocks, and the Markov offsets
+__global__ void pose_pack_kernel(const double *mu, const double *cov, long long cov_stride, double *state, double *offsets,
+                                 long long first, long long count) {
+  long long total = count * pose::BLK;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    long long f = g / pose::BLK;
+    int k = (int)(g - f * pose::BLK);
+    double v = 0.0;
+    if (k < pose::DIM) {
+      v = mu[f * pose::DIM + k];
+      if (k >= pose::P_INERTIA && k < pose::P_WV) offsets[(first + f) * pose::NOFF + (k - pose::P_INERTIA)] = v;
+      if (k == pose::P_RHO) offsets[(first + f) * pose::NOFF + 27] = v;
+    } else if (k >= pose::OFF_S && k < pose::OFF_S + pose::NP) {
+      unsigned ij = g_lut[k - pose::OFF_S];
+      int i = ij & 0xff, j = ij >> 8;
+      v = cov[f * cov_stride + i * pose::N + j];
+    }
+    state[(first + f) * pose::BLK + k] = v;
+  }
+}
+__global__ void pose_unpack_kernel(const double *state, double *mu, double *cov, long long first, long long count) {
+  if (mu) {
+    long long total = count * pose::DIM;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+      long long f = g / pose::DIM;
+      int k = (int)(g - f * pose::DIM);
+      mu[g] = state[(first + f) * pose::BLK + k];
+    }
+  }
+  if (cov) {
+    long long total = count * pose::N * pose::N;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+      long long f = g / (pose::N * pose::N);
+      int k = (int)(g - f * pose::N * pose::N);
+      int i = k / pose::N, j = k - i * pose::N;
+      cov[g] = state[(first + f) * pose::BLK + pose::OFF_S + pose::sidx(i, j)];
+    }
+  }
+}
+__global__ void pose_set_pose_kernel(double *state, const double *pose7, long long B) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < B * 7) { long long f = g / 7; int k = (int)(g - f * 7); state[f * pose::BLK + k] = pose7[g]; }
+}
+// getRotationRate(), reference src/PoseUKF.cpp:693-699
+__global__ void pose_rotation_rate_kernel(const double *state, const double *rot_rate, double *out, long long B,
+                                          const __grid_constant__ pose::Params P) {
+  long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  const double *mu = state + f * pose::BLK;
+  double lat = tmerc_nav_to_lat(P.tm, mu[0], mu[1]);
+  Vec3 eb = qrot_inv(Quat{mu[3], mu[4], mu[5], mu[6]}, Vec3{kEarthW * cos(lat), 0.0, kEarthW * sin(lat)});
+  out[f * 3 + 0] = rot_rate[f * 3 + 0] - mu[pose::P_BG + 0] - eb.x;
+  out[f * 3 + 1] = rot_rate[f * 3 + 1] - mu[pose::P_BG + 1] - eb.y;
+  out[f * 3 + 2] = rot_rate[f * 3 + 2] - mu[pose::P_BG + 2] - eb.z;
+}
+
+// ensemble statistics: out = [count, sum mu (DIM), sum mu mu^T (lower, row-major packed)]
+template <int DIM>
+__global__ void ensemble_stats_kernel(const double *state, long long stride, long long B, double *out) {
+  constexpr int NOUT = 1 + DIM + DIM * (DIM + 1) / 2;
+  constexpr int PER = (NOUT + 255) / 256;
+  __shared__ double m[DIM];
+  double acc[PER];
+  int ia[PER], ib[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    acc[k] = 0.0;
+    int o = threadIdx.x + 256 * k;
+    ia[k] = -2; ib[k] = 0;
+    if (o == 0) ia[k] = -1;
+    else if (o <= DIM) { ia[k] = o - 1; ib[k] = -1; }
+    else if (o < NOUT) {
+      int e = o - 1 - DIM, i = 0;
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      ia[k] = i; ib[k] = e - i * (i + 1) / 2;
+    }
+  }
+  for (long long f = blockIdx.x; f < B; f += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < DIM) m[threadIdx.x] = state[f * stride + threadIdx.x];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (ia[k] == -1) acc[k] += 1.0;
+      else if (ia[k] >= 0) acc[k] += (ib[k] < 0) ? m[ia[k]] : m[ia[k]] * m[ib[k]];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    int o = threadIdx.x + 256 * k;
+    if (o < NOUT) atomicAdd(out + o, acc[k]);
+  }
+}
+
+}  // namespace
+
+// ======================================================================================================
+struct uwvkf_filter_s {
+  int kind = 0;
+  int64_t B = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // PoseUKF
+  double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr;
+  uint32_t *d_status = nullptr;
+  double *d_z = nullptr, *d_Rpf = nullptr, *d_w = nullptr;  // staging for host inputs
+  uint8_t *d_valid = nullptr;
+  double *d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  pose::Params pp{};
+  bool have_params = false, have_Q = false;
+};
+
+namespace {
+
+constexpr int kFastWarps = 12, kSlowWarps = 6;
+constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
+
+int ensure_tmp(uwvkf_handle h, size_t bytes) {
+  if (h->tmp_bytes >= bytes) return UWVKF_OK;
+  if (h->d_tmp) cudaFree(h->d_tmp);
+  h->d_tmp = nullptr; h->tmp_bytes = 0;
+  CK(cudaMalloc(&h->d_tmp, bytes));
+  h->tmp_bytes = bytes;
+  return UWVKF_OK;
+}
+
+void fill_tmerc(TMercConst &tm, double lat0, double lon0) {
+  const double a = 6378137.0, f = 1.0 / 298.257223563;
+  const double n = f / (2 - f), n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
+  tm.lat0 = lat0; tm.lon0 = lon0;
+  tm.e = std::sqrt(f * (2 - f));
+  tm.A = a / (1 + n) * (1 + n2 / 4 + n4 / 64 + n6 / 256);
+  tm.Ainv = 1.0 / tm.A;
+  double *al = tm.alpha, *be = tm.beta, *de = tm.delta;
+  al[0] = n / 2 - 2 * n2 / 3 + 5 * n3 / 16 + 41 * n4 / 180 - 127 * n5 / 288 + 7891 * n6 / 37800;
+  al[1] = 13 * n2 / 48 - 3 * n3 / 5 + 557 * n4 / 1440 + 281 * n5 / 630 - 1983433 * n6 / 1935360;
+  al[2] = 61 * n3 / 240 - 103 * n4 / 140 + 15061 * n5 / 26880 + 167603 * n6 / 181440;
+  al[3] = 49561 * n4 / 161280 - 179 * n5 / 168 + 6601661 * n6 / 7257600;
+  al[4] = 34729 * n5 / 80640 - 3418889 * n6 / 1995840;
+  al[5] = 212378941 * n6 / 319334400;
+  be[0] = n / 2 - 2 * n2 / 3 + 37 * n3 / 96 - n4 / 360 - 81 * n5 / 512 + 96199 * n6 / 604800;
+  be[1] = n2 / 48 + n3 / 15 - 437 * n4 / 1440 + 46 * n5 / 105 - 1118711 * n6 / 3870720;
+  be[2] = 17 * n3 / 480 - 37 * n4 / 840 - 209 * n5 / 4480 + 5569 * n6 / 90720;
+  be[3] = 4397 * n4 / 161280 - 11 * n5 / 504 - 830251 * n6 / 7257600;
+  be[4] = 4583 * n5 / 161280 - 108847 * n6 / 3991680;
+  be[5] = 20648693 * n6 / 638668800;
+  de[0] = 2 * n - 2 * n2 / 3 - 2 * n3 + 116 * n4 / 45 + 26 * n5 / 45 - 2854 * n6 / 675;
+  de[1] = 7 * n2 / 3 - 8 * n3 / 5 - 227 * n4 / 45 + 2704 * n5 / 315 + 2323 * n6 / 945;
+  de[2] = 56 * n3 / 15 - 136 * n4 / 35 - 1262 * n5 / 105 + 73814 * n6 / 2835;
+  de[3] = 4279 * n4 / 630 - 332 * n5 / 35 - 399572 * n6 / 14175;
+  de[4] = 4174 * n5 / 315 - 144838 * n6 / 6237;
+  de[5] = 601676 * n6 / 22275;
+  double tau = std::tan(lat0);
+  double sig = std::sinh(tm.e * std::atanh(tm.e * tau / std::sqrt(1 + tau * tau)));
+  double taup = tau * std::sqrt(1 + sig * sig) - sig * std::sqrt(1 + tau * tau);
+  double chi0 = std::atan(taup), s = chi0;
+  for (int j = 0; j < 6; ++j) s += al[j] * std::sin(2 * (j + 1) * chi0);
+  tm.xi0 = s;
+}
+
+int meas_dim(int kind) {
+  switch (kind) {
+    case UWVKF_POSE_XY: case UWVKF_POSE_WATER_VELOCITY: case UWVKF_POSE_GEOGRAPHIC: case UWVKF_POSE_DELAYED_XY: return 2;
+    case UWVKF_POSE_Z: case UWVKF_POSE_PRESSURE: return 1;
+    case UWVKF_POSE_ACCELERATION: case UWVKF_POSE_VELOCITY: return 3;
+  }
+  return -1;
+}
+
+template <int KMAX, int WARPS>
+int launch_pose(uwvkf_handle h, const pose::Launch &L) {
+  using W = pose::WL<KMAX>;
+  size_t smem = (size_t)(1432 + 360 + WARPS * W::TOTAL) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(pose_step_kernel<KMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  long long need = (L.B + WARPS - 1) / WARPS;
+  int grid = (int)std::min<long long>(need, h->sm_count);
+  pose_step_kernel<KMAX, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return UWVKF_OK;
+}
+
+int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
+  if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
+  pose::Launch L{};
+  L.state = h->d_state; L.offsets = h->d_offsets; L.rot_rate = h->d_rot; L.status = h->d_status; L.Q = h->d_Q;
+  L.B = h->B; L.nops = nops;
+  bool slow = false;
+  for (int o = 0; o < nops; ++o) {
+    L.ops[o] = ops[o];
+    if (ops[o].type == 0 && !h->have_Q) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_set_process_noise was not called");
+    if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_PRESSURE || ops[o].kind == UWVKF_POSE_WATER_VELOCITY)) slow = true;
+  }
+  return slow ? launch_pose<53, kSlowWarps>(h, L) : launch_pose<19, kFastWarps>(h, L);
+}
+
+// stage a host/device input array on the device; returns the device pointer to use
+int stage(uwvkf_handle h, const void *src, size_t bytes, size_t cap, int memspace, void **slot, const void **out) {
+  if (!src) { *out = nullptr; return UWVKF_OK; }
+  if (memspace == UWVKF_DEVICE) { *out = src; return UWVKF_OK; }
+  if (!*slot) CK(cudaMalloc(slot, cap));
+  CK(cudaMemcpyAsync(*slot, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  *out = *slot;
+  return UWVKF_OK;
+}
+
+int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, int R_per_filter, const double *aux,
+                   const uint8_t *valid, int memspace, pose::Op &op) {
+  const int m = meas_dim(kind);
+  if (m < 0) return fail(UWVKF_ERR_INVALID_ARGUMENT, "unknown PoseUKF measurement kind");
+  if (!z || !R) return fail(UWVKF_ERR_INVALID_ARGUMENT, "z and R must not be NULL");
+  std::memset(&op, 0, sizeof op);
+  op.type = 1; op.kind = kind;
+  // checkMeasurment(): NaN in mu or cov throws in the reference.  Host inputs of small batches are checked
+  // here; every input is also checked per filter on the device (UWVKF_ST_NAN_MEASUREMENT).
+  if (memspace == UWVKF_HOST && h->B <= 1024) {
+    for (int64_t k = 0; k < h->B * m; ++k) if (std::isnan(z[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
+  }
+  if (!R_per_filter || memspace == UWVKF_HOST) {
+    int64_t nr = R_per_filter ? h->B * m * m : m * m;
+    if (nr <= 1024 * 9) for (int64_t k = 0; k < nr; ++k) if (std::isnan(R[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement covariance contains NaN");
+  }
+  const void *p;
+  int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * 3 * sizeof(double), memspace, (void **)&h->d_z, &p);
+  if (rc) return rc;
+  op.z = (const double *)p;
+  if (R_per_filter) {
+    rc = stage(h, R, (size_t)h->B * m * m * sizeof(double), (size_t)h->B * 9 * sizeof(double), memspace, (void **)&h->d_Rpf, &p);
+    if (rc) return rc;
+    op.Rdev = (const double *)p;
+  } else {
+    for (int k = 0; k < m * m; ++k) op.R[k] = R[k];
+  }
+  rc = stage(h, valid, (size_t)h->B, (size_t)h->B, memspace, (void **)&h->d_valid, &p);
+  if (rc) return rc;
+  op.valid = (const uint8_t *)p;
+  if (aux) {
+    int na = (kind == UWVKF_POSE_WATER_VELOCITY) ? 1 : (kind == UWVKF_POSE_DELAYED_XY ? 2 : 3);
+    for (int k = 0; k < na; ++k) { if (std::isnan(aux[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "aux contains NaN"); op.aux[k] = aux[k]; }
+  } else if (kind == UWVKF_POSE_WATER_VELOCITY || kind == UWVKF_POSE_DELAYED_XY) {
+    return fail(UWVKF_ERR_INVALID_ARGUMENT, "this measurement kind needs aux");
+  }
+  return UWVKF_OK;
+}
+
+#define REQUIRE(h, k)                                                                  \
+  if (!(h)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");                    \
+  if ((h)->kind != (k)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "wrong filter kind for this call"); \
+  CK(cudaSetDevice((h)->device));
+
+}  // namespace
+
+extern "C" {
+
+const char *uwvkf_last_error(void) { return g_err.c_str(); }
+const char *uwvkf_version(void) { return "uwvkf 0.1 (sm_100a)"; }
+
+int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) {
+  if (!out || batch <= 0) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (filter_kind != UWVKF_FILTER_POSE) return fail(UWVKF_ERR_UNSUPPORTED, "filter kind not built yet");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(UWVKF_ERR_NO_DEVICE, "no CUDA device: uwvkf has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad device index");
+  CK(cudaSetDevice(device));
+  uwvkf_handle h = new uwvkf_filter_s();
+  h->kind = filter_kind; h->B = batch; h->device = device;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  std::vector<uint16_t> lut(pose::NP);
+  for (int j = 0; j < pose::N; ++j) for (int i = j; i < pose::N; ++i) lut[pose::cidx(i, j)] = (uint16_t)(i | (j << 8));
+  cudaError_t ce = cudaMemcpyToSymbol(g_lut, lut.data(), lut.size() * sizeof(uint16_t));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_state, (size_t)batch * pose::BLK * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_offsets, (size_t)batch * pose::NOFF * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_rot, (size_t)batch * 3 * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_status, (size_t)batch * sizeof(uint32_t));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_Q, (size_t)pose::NP * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_state, 0, (size_t)batch * pose::BLK * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_offsets, 0, (size_t)batch * pose::NOFF * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_rot, 0, (size_t)batch * 3 * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_status, 0, (size_t)batch * sizeof(uint32_t));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_Q, 0, (size_t)pose::NP * sizeof(double));
+  if (ce != cudaSuccess) {
+    std::string msg = cudaGetErrorString(ce);
+    uwvkf_destroy(h);
+    return fail(UWVKF_ERR_CUDA, "allocation failed: " + msg);
+  }
+  h->pp.mean_tol = 1e-9;
+  h->pp.mean_max_it = 100;
+  *out = h;
+  return UWVKF_OK;
+}
+
+int uwvkf_destroy(uwvkf_handle h) {
+  if (!h) return UWVKF_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
+  cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_w); cudaFree(h->d_valid); cudaFree(h->d_tmp);
+  delete h;
+  return UWVKF_OK;
+}
+
+int uwvkf_set_stream(uwvkf_handle h, void *s) {
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  h->stream = (cudaStream_t)s;
+  return UWVKF_OK;
+}
+int uwvkf_synchronize(uwvkf_handle h) {
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+int64_t uwvkf_batch(uwvkf_handle h) { return h ? h->B : 0; }
+int64_t uwvkf_kernel_launches(uwvkf_handle h) { return h ? h->launches : 0; }
+
+int uwvkf_set_mean_policy(uwvkf_handle h, double tol, int max_it) {
+  if (!h || max_it < 1 || !(tol >= 0)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad policy");
+  h->pp.mean_tol = tol; h->pp.mean_max_it = max_it;
+  return UWVKF_OK;
+}
+
+int uwvkf_set_state(uwvkf_handle h, const double *mu, const double *cov, int64_t cov_stride, int64_t first, int64_t count,
+                    int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!mu || !cov || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad range or null pointer");
+  if (cov_stride != 0 && cov_stride != pose::N * pose::N) return fail(UWVKF_ERR_INVALID_ARGUMENT, "cov_stride must be 0 (shared) or DOF*DOF");
+  const size_t cb = (size_t)pose::N * pose::N * sizeof(double), mb = (size_t)pose::DIM * sizeof(double);
+  if (memspace == UWVKF_DEVICE) {
+    pose_pack_kernel<<<1024, 256, 0, h->stream>>>(mu, cov, cov_stride, h->d_state, h->d_offsets, first, count);
+    CK(cudaGetLastError());
+    h->launches++;
+    return UWVKF_OK;
+  }
+  int64_t chunk = std::min<int64_t>(count, kChunk);
+  size_t need = (size_t)chunk * mb + (cov_stride ? (size_t)chunk * cb : cb);
+  int rc = ensure_tmp(h, need);
+  if (rc) return rc;
+  double *dmu = h->d_tmp, *dcov = h->d_tmp + (size_t)chunk * pose::DIM;
+  if (!cov_stride) CK(cudaMemcpyAsync(dcov, cov, cb, cudaMemcpyHostToDevice, h->stream));
+  for (int64_t o = 0; o < count; o += chunk) {
+    int64_t c = std::min<int64_t>(chunk, count - o);
+    CK(cudaMemcpyAsync(dmu, mu + o * pose::DIM, (size_t)c * mb, cudaMemcpyHostToDevice, h->stream));
+    if (cov_stride) CK(cudaMemcpyAsync(dcov, cov + o * cov_stride, (size_t)c * cb, cudaMemcpyHostToDevice, h->stream));
+    pose_pack_kernel<<<1024, 256, 0, h->stream>>>(dmu, dcov, cov_stride, h->d_state, h->d_offsets, first + o, c);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next chunk
+  }
+  return UWVKF_OK;
+}
+
+int uwvkf_get_state(uwvkf_handle h, double *mu, double *cov, int64_t first, int64_t count, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if ((!mu && !cov) || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad range or null pointer");
+  const size_t cb = (size_t)pose::N * pose::N * sizeof(double), mb = (size_t)pose::DIM * sizeof(double);
+  if (memspace == UWVKF_DEVICE) {
+    pose_unpack_kernel<<<1024, 256, 0, h->stream>>>(h->d_state, mu, cov, first, count);
+    CK(cudaGetLastError());
+    h->launches++;
+    return UWVKF_OK;
+  }
+  int64_t chunk = std::min<int64_t>(count, cov ? kChunk : (int64_t)1 << 20);
+  int rc = ensure_tmp(h, (size_t)chunk * (mb + (cov ? cb : 0)));
+  if (rc) return rc;
+  double *dmu = h->d_tmp, *dcov = cov ? h->d_tmp + (size_t)chunk * pose::DIM : nullptr;
+  for (int64_t o = 0; o < count; o += chunk) {
+    int64_t c = std::min<int64_t>(chunk, count - o);
+    pose_unpack_kernel<<<1024, 256, 0, h->stream>>>(h->d_state, mu ? dmu : nullptr, dcov, first + o, c);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (mu) CK(cudaMemcpyAsync(mu + o * pose::DIM, dmu, (size_t)c * mb, cudaMemcpyDeviceToHost, h->stream));
+    if (cov) CK(cudaMemcpyAsync(cov + o * pose::N * pose::N, dcov, (size_t)c * cb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return UWVKF_OK;
+}
+
+int uwvkf_set_process_noise(uwvkf_handle h, const double *Q) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!Q) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null Q");
+  std::vector<double> packed(pose::NP);
+  for (int j = 0; j < pose::N; ++j) for (int i = j; i < pose::N; ++i) packed[pose::cidx(i, j)] = Q[i * pose::N + j];
+  CK(cudaMemcpyAsync(h->d_Q, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_Q = true;
+  return UWVKF_OK;
+}
+
+int uwvkf_get_status(uwvkf_handle h, uint32_t *status, int64_t first, int64_t count) {
+  if (!h || !status || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(status, h->d_status + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+int uwvkf_clear_status(uwvkf_handle h) {
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_status, 0, (size_t)h->B * sizeof(uint32_t), h->stream));
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_set_params(uwvkf_handle h, const double *p) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!p) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null params");
+  pose::Params &P = h->pp;
+  fill_tmerc(P.tm, p[UWVKF_PP_LAT0], p[UWVKF_PP_LON0]);
+  P.gyro_bias_tau = p[UWVKF_PP_GYRO_BIAS_TAU];
+  P.acc_bias_tau = p[UWVKF_PP_ACC_BIAS_TAU];
+  for (int k = 0; k < 3; ++k) {
+    P.gyro_bias_offset[k] = p[UWVKF_PP_GYRO_BIAS_OFFSET + k];
+    P.acc_bias_offset[k] = p[UWVKF_PP_ACC_BIAS_OFFSET + k];
+    P.imu_in_body[k] = p[UWVKF_PP_IMU_IN_BODY + k];
+  }
+  P.inertia_tau = p[UWVKF_PP_INERTIA_TAU]; P.lin_damping_tau = p[UWVKF_PP_LIN_DAMPING_TAU];
+  P.quad_damping_tau = p[UWVKF_PP_QUAD_DAMPING_TAU]; P.wv_tau = p[UWVKF_PP_WV_TAU]; P.wv_limits = p[UWVKF_PP_WV_LIMITS];
+  P.wv_scale = p[UWVKF_PP_WV_SCALE]; P.adcp_bias_tau = p[UWVKF_PP_ADCP_BIAS_TAU];
+  P.atm_pressure = p[UWVKF_PP_ATM_PRESSURE]; P.rho_tau = p[UWVKF_PP_WATER_DENSITY_TAU];
+  h->have_params = true;
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_set_offsets(uwvkf_handle h, const double *offsets, int64_t first, int64_t count) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!offsets || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  CK(cudaMemcpyAsync(h->d_offsets + first * pose::NOFF, offsets, (size_t)count * pose::NOFF * sizeof(double),
+                     cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_set_rotation_rate(uwvkf_handle h, const double *w, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!w) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null rotation rate");
+  if (memspace == UWVKF_HOST && h->B <= 1024)
+    for (int64_t k = 0; k < h->B * 3; ++k) if (std::isnan(w[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "rotation rate contains NaN");
+  CK(cudaMemcpyAsync(h->d_rot, w, (size_t)h->B * 3 * sizeof(double),
+                     memspace == UWVKF_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_get_rotation_rate(uwvkf_handle h, double *out) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!out) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null output");
+  if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
+  int rc = ensure_tmp(h, (size_t)h->B * 3 * sizeof(double));
+  if (rc) return rc;
+  pose_rotation_rate_kernel<<<(unsigned)((h->B + 127) / 128), 128, 0, h->stream>>>(h->d_state, h->d_rot, h->d_tmp, h->B, h->pp);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaMemcpyAsync(out, h->d_tmp, (size_t)h->B * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+
+int uwvkf_predict(uwvkf_handle h, double dt) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (std::isnan(dt)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "dt is NaN");
+  pose::Op op{};
+  op.type = 0; op.dt = dt;
+  return run_pose(h, 1, &op);
+}
+
+int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const double *R, int R_per_filter, const double *aux,
+                      const uint8_t *valid, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  pose::Op op;
+  int rc = make_update_op(h, meas_kind, z, R, R_per_filter, aux, valid, memspace, op);
+  if (rc) return rc;
+  return run_pose(h, 1, &op);
+}
+
+int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int meas_kind, const double *z, const double *R,
+                              int R_per_filter, const double *aux, const uint8_t *valid, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (std::isnan(dt)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "dt is NaN");
+  if (w) {
+    int rc = uwvkf_pose_set_rotation_rate(h, w, memspace);
+    if (rc) return rc;
+  }
+  pose::Op ops[2];
+  std::memset(&ops[0], 0, sizeof ops[0]);
+  ops[0].type = 0; ops[0].dt = dt;
+  int rc = make_update_op(h, meas_kind, z, R, R_per_filter, aux, valid, memspace, ops[1]);
+  if (rc) return rc;
+  return run_pose(h, 2, ops);
+}
+
+int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose7) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!pose7) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null pose");
+  int rc = ensure_tmp(h, (size_t)h->B * 7 * sizeof(double));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tmp, pose7, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  pose_set_pose_kernel<<<(unsigned)((h->B * 7 + 255) / 256), 256, 0, h->stream>>>(h->d_state, h->d_tmp, h->B);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+
+int64_t uwvkf_ensemble_stats_size(uwvkf_handle h) {
+  if (!h) return 0;
+  return 1 + pose::DIM + pose::DIM * (pose::DIM + 1) / 2;
+}
+
+int uwvkf_ensemble_stats(uwvkf_handle h, double *out, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!out) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null output");
+  const size_t bytes = (size_t)uwvkf_ensemble_stats_size(h) * sizeof(double);
+  double *dout = out;
+  if (memspace == UWVKF_HOST) {
+    int rc = ensure_tmp(h, bytes);
+    if (rc) return rc;
+    dout = h->d_tmp;
+  }
+  CK(cudaMemsetAsync(dout, 0, bytes, h->stream));
+  int grid = (int)std::min<int64_t>(h->B, (int64_t)h->sm_count * 8);
+  ensemble_stats_kernel<pose::DIM><<<grid, 256, 0, h->stream>>>(h->d_state, pose::BLK, h->B, dout);
+  CK(cudaGetLastError());
+  h->launches++;
+  if (memspace == UWVKF_HOST) {
+    CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return UWVKF_OK;
+}
+
+}  // extern "C"

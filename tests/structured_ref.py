@@ -88,7 +88,7 @@ def tangent_to_stored(t):
     return t if t < 3 else t + 1  # orientation takes 4 stored slots at 3..6
 
 
-def pose_predict(mu, S, Q, w_meas, par, offsets, dt, nav_lat, tol=1e-11, max_it=100):
+def pose_predict(mu, S, Q, w_meas, par, offsets, dt, nav_lat, tol=1e-9, max_it=100):
     """Structured PoseUKF predict. nav_lat(x, y) -> latitude.  par: flat PoseUKFParameter (22)."""
     k = 15
     L = chol_leading(S, k)
@@ -156,7 +156,7 @@ def pose_predict(mu, S, Q, w_meas, par, offsets, dt, nav_lat, tol=1e-11, max_it=
     return mn, Sn
 
 
-def apply_delta(mu, S, delta, tol=1e-11, max_it=100):
+def apply_delta(mu, S, delta, tol=1e-9, max_it=100):
     k = 6
     L = chol_leading(S, k)
     q = mu[3:7]
@@ -179,7 +179,7 @@ def apply_delta(mu, S, delta, tol=1e-11, max_it=100):
     return mn, Sn
 
 
-def pose_update(mu, S, z, R, h, k, gate=None, tol=1e-11, max_it=100):
+def pose_update(mu, S, z, R, h, k, gate=None, tol=1e-9, max_it=100):
     """Structured update for a vector measurement whose model h(mu, d) depends on the first k tangent coordinates.
     h(mu, d): evaluate the measurement at mu (+) d where d is a length-k perturbation of the leading coordinates."""
     L = chol_leading(S, k)

@@ -1,0 +1,320 @@
+"""GPU parity tests of the PoseUKF hot path: CUDA engine (through the C ABI) vs the CPU oracle.
+
+Tolerances are BASELINE.json's north_star: <= 1e-9 relative on the state and <= 1e-8 on the covariance per step.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from parity import TOL_COV, TOL_STATE, cov_err, cov_err_scaled, state_err
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.01
+
+
+@pytest.fixture(scope="module")
+def scen(syn):
+    cfg = syn.pose_config()
+    par = syn.pose_params(cfg)
+    Q = syn.pose_process_noise(cfg, DT)
+    return dict(cfg=cfg, par=par, Q=Q)
+
+
+def make_batch(pkg, syn, scen, B, first_filter=0):
+    filt = np.arange(first_filter, first_filter + B)
+    mu, cov = syn.pose_initial_batch(filt, scen["cfg"])
+    ukf = pkg.PoseUKFBatch(B, scen["par"])
+    ukf.set_process_noise(scen["Q"])
+    ukf.set_state(mu, cov)
+    offsets = np.concatenate([mu[:, 20:47], mu[:, 53:54]], axis=1)
+    return ukf, filt, mu, cov, offsets
+
+
+def oracle_predict(mu, cov, scen, w, offsets, dt=DT):
+    out_mu, out_cov = np.empty_like(mu), np.empty_like(cov)
+    for f in range(mu.shape[0]):
+        out_mu[f], out_cov[f], st, _ = orc.pose_predict(mu[f], cov[f], scen["Q"], w[f], scen["par"], offsets[f], dt)
+        assert st == 0
+    return out_mu, out_cov
+
+
+def oracle_update(kind, mu, cov, scen, z, R, aux, w, valid=None):
+    out_mu, out_cov = mu.copy(), cov.copy()
+    sts = np.zeros(mu.shape[0], dtype=np.int64)
+    for f in range(mu.shape[0]):
+        if valid is not None and not valid[f]:
+            continue
+        Rf = R[f] if R.ndim == 3 else R
+        out_mu[f], out_cov[f], sts[f], _ = orc.pose_update(kind, mu[f], cov[f], z[f], Rf, aux, w[f], scen["par"])
+    return out_mu, out_cov, sts
+
+
+def assert_parity(gmu, gcov, omu, ocov, what):
+    worst = (0.0, 0.0, 0.0)
+    for f in range(gmu.shape[0]):
+        e = (state_err(gmu[f], omu[f]), cov_err(gcov[f], ocov[f]), cov_err_scaled(gcov[f], ocov[f]))
+        worst = tuple(max(a, b) for a, b in zip(worst, e))
+    print(f"[parity] {what}: state {worst[0]:.2e}  cov {worst[1]:.2e}  cov(scaled) {worst[2]:.2e}")
+    assert worst[0] <= TOL_STATE, f"{what}: state error {worst[0]:.3e}"
+    assert worst[1] <= TOL_COV, f"{what}: covariance error {worst[1]:.3e}"
+    assert np.allclose(gcov, np.swapaxes(gcov, 1, 2)), "covariance getter must return a symmetric matrix"
+    return worst
+
+
+def test_set_get_roundtrip(pkg, syn, scen):
+    ukf, _, mu, cov, _ = make_batch(pkg, syn, scen, 37)
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(37, 53, 53))
+    cov = A @ np.swapaxes(A, 1, 2)
+    ukf.set_state(mu, cov)
+    gmu, gcov = ukf.get_state()
+    assert np.array_equal(gmu, mu)
+    assert np.array_equal(gcov, np.tril(cov) + np.swapaxes(np.tril(cov, -1), 1, 2))
+    # partial ranges and the shared-covariance form
+    ukf.set_state(mu[5:9] + 1.0, cov[0], first=5)
+    gmu2, gcov2 = ukf.get_state(first=4, count=6)
+    assert np.array_equal(gmu2[0], mu[4]) and np.array_equal(gmu2[1:5], mu[5:9] + 1.0) and np.array_equal(gmu2[5], mu[9])
+    assert np.array_equal(gcov2[2], gcov[0])
+    ukf.close()
+
+
+def test_predict_parity(pkg, syn, scen):
+    B = 48
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    w = syn.pose_inputs(filt, 1)["gyro"]
+    ukf.integrate_rotation_rate(w)
+    ukf.prediction_step(DT)
+    gmu, gcov = ukf.get_state()
+    omu, ocov = oracle_predict(mu, cov, scen, w, off)
+    assert_parity(gmu, gcov, omu, ocov, "predict from block-diagonal Sigma0")
+    assert not ukf.get_status().any()
+    # second predict from a now dense covariance
+    ukf.prediction_step(DT)
+    gmu2, gcov2 = ukf.get_state()
+    omu2, ocov2 = oracle_predict(gmu, gcov, scen, w, off)
+    assert_parity(gmu2, gcov2, omu2, ocov2, "predict from dense Sigma")
+    ukf.close()
+
+
+def _dense_state(pkg, syn, scen, B, steps=3):
+    """A batch a few fused steps into the run, so that Sigma is dense and correlations are realistic."""
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    for s in range(1, steps + 1):
+        inp = syn.pose_inputs(filt, s)
+        ukf.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        ukf.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+    return ukf, filt, off
+
+
+@pytest.mark.parametrize("kind", ["velocity", "acceleration", "xy", "z", "pressure", "adcp", "geographic", "delayed_xy"])
+def test_update_parity(pkg, syn, scen, kind):
+    B = 24
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    inp = syn.pose_inputs(filt, 4)
+    w = inp["gyro"]
+    ukf.integrate_rotation_rate(w)
+    truth = syn.truth(4 * DT)
+    rng = np.random.default_rng(5)
+    aux = None
+    if kind == "velocity":
+        k, z, R = pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL
+    elif kind == "acceleration":
+        k, z, R = pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC
+    elif kind == "xy":
+        k, z, R = pkg.POSE_XY, mu[:, 0:2] + 0.1 * rng.normal(size=(B, 2)), np.array([[0.04, 0.01], [0.01, 0.09]])
+    elif kind == "z":
+        k, z, R = pkg.POSE_Z, (truth["z"] + 0.05 * rng.normal(size=(B, 1))), np.array([[0.0025]])
+    elif kind == "pressure":
+        k, z, R, aux = pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE, np.array([0.3, -0.1, 0.2])
+    elif kind == "adcp":
+        k, z, R, aux = pkg.POSE_WATER_VELOCITY, inp["adcp"], syn.R_ADCP, np.array([0.5])
+    elif kind == "geographic":
+        ll = np.stack([orc.tmerc_nav_to_world(syn.LAT0, syn.LON0, mu[f, 0] + 0.3, mu[f, 1] - 0.2) for f in range(B)])
+        k, z, R, aux = pkg.POSE_GEOGRAPHIC, ll, np.array([[1.0, 0.0], [0.0, 1.0]]), np.array([0.5, 0.1, -0.3])
+    else:
+        k, z, R, aux = pkg.POSE_DELAYED_XY, mu[:, 0:2] + 0.05, np.array([[0.04, 0.0], [0.0, 0.04]]), np.array([0.1, -0.2])
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    ukf.integrate_measurement(k, z, R, aux=aux)
+    gmu, gcov = ukf.get_state()
+    omu, ocov, sts = oracle_update(k, mu, cov, scen, z, R, aux, w)
+    gst = ukf.get_status()
+    assert np.array_equal(gst & 4 != 0, sts & 4 != 0), "gate decisions differ"
+    assert not (gst & ~np.uint32(4)).any()
+    assert_parity(gmu, gcov, omu, ocov, f"update {kind}")
+    ukf.close()
+
+
+def test_fused_step_equals_separate_calls(pkg, syn, scen):
+    B = 40
+    a, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    b, *_ = make_batch(pkg, syn, scen, B)
+    for s in range(1, 4):
+        inp = syn.pose_inputs(filt, s)
+        a.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        b.integrate_rotation_rate(inp["gyro"])
+        b.prediction_step(DT)
+        b.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    a.close(); b.close()
+
+
+def test_lockstep_sequence_parity(pkg, syn, scen):
+    """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
+    step so that the asserted error is the per-step error of north_star."""
+    B, STEPS = 8, 40
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    worst = np.zeros(3)
+    for s in range(1, STEPS + 1):
+        inp = syn.pose_inputs(filt, s)
+        w = inp["gyro"]
+        mu, cov = ukf.get_state()
+        ukf.predict_update(DT, w, pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        ukf.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+        omu, ocov = oracle_predict(mu, cov, scen, w, off)
+        omu, ocov, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, inp["dvl"], syn.R_DVL, None, w)
+        omu, ocov, _ = oracle_update(orc.ACCELERATION, omu, ocov, scen, inp["acc"], syn.R_ACC, None, w)
+        if s % 10 == 0:
+            ukf.integrate_measurement(pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE)
+            ukf.integrate_measurement(pkg.POSE_WATER_VELOCITY, inp["adcp"], syn.R_ADCP, aux=np.array([0.5]))
+            omu, ocov, _ = oracle_update(orc.PRESSURE, omu, ocov, scen, inp["pressure"], syn.R_PRESSURE, None, w)
+            omu, ocov, _ = oracle_update(orc.WATER_VELOCITY, omu, ocov, scen, inp["adcp"], syn.R_ADCP, np.array([0.5]), w)
+        gmu, gcov = ukf.get_state()
+        worst = np.maximum(worst, assert_parity(gmu, gcov, omu, ocov, f"step {s}"))
+    print(f"[parity] lockstep worst over {STEPS} steps: state {worst[0]:.2e} cov {worst[1]:.2e} cov(scaled) {worst[2]:.2e}")
+    assert not (ukf.get_status() & ~np.uint32(4)).any()
+    ukf.close()
+
+
+def test_free_running_drift(pkg, syn, scen):
+    """GPU and oracle run independently for 300 steps from the same start: drift is reported and loosely bounded."""
+    B, STEPS = 4, 300
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    omu, ocov = mu.copy(), cov.copy()
+    for s in range(1, STEPS + 1):
+        inp = syn.pose_inputs(filt, s)
+        w = inp["gyro"]
+        ukf.predict_update(DT, w, pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        omu, ocov = oracle_predict(omu, ocov, scen, w, off)
+        omu, ocov, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, inp["dvl"], syn.R_DVL, None, w)
+    gmu, gcov = ukf.get_state()
+    es = max(state_err(gmu[f], omu[f]) for f in range(B))
+    ec = max(cov_err(gcov[f], ocov[f]) for f in range(B))
+    print(f"[drift] {STEPS} free-running steps: state {es:.2e} cov {ec:.2e}")
+    assert es < 1e-7 and ec < 1e-6
+    ukf.close()
+
+
+def test_valid_mask_and_per_filter_R(pkg, syn, scen):
+    B = 16
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    inp = syn.pose_inputs(filt, 4)
+    valid = (np.arange(B) % 3 != 0).astype(np.uint8)
+    R = np.stack([syn.R_DVL * (1 + f) for f in range(B)])
+    ukf.integrate_rotation_rate(inp["gyro"])
+    ukf.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], R, valid=valid)
+    gmu, gcov = ukf.get_state()
+    omu, ocov, _ = oracle_update(orc.VELOCITY, mu, cov, scen, inp["dvl"], R, None, inp["gyro"], valid=valid)
+    assert np.array_equal(gmu[valid == 0], mu[valid == 0]) and np.array_equal(gcov[valid == 0], cov[valid == 0])
+    assert_parity(gmu, gcov, omu, ocov, "masked update with per-filter R")
+    ukf.close()
+
+
+def test_gate_rejects_outlier(pkg, syn, scen):
+    B = 8
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    inp = syn.pose_inputs(filt, 4)
+    z = inp["adcp"].copy()
+    z[::2] += 5.0  # gross outliers on the even filters
+    ukf.integrate_measurement(pkg.POSE_WATER_VELOCITY, z, syn.R_ADCP, aux=np.array([0.5]))
+    gmu, gcov = ukf.get_state()
+    st = ukf.get_status()
+    assert (st[::2] & pkg.ST_GATE_REJECTED).all() and not (st[1::2] & pkg.ST_GATE_REJECTED).any()
+    assert np.array_equal(gmu[::2], mu[::2]) and np.array_equal(gcov[::2], cov[::2])
+    assert not np.array_equal(gmu[1::2], mu[1::2])
+    ukf.clear_status()
+    assert not ukf.get_status().any()
+    ukf.close()
+
+
+def test_nan_measurement_is_refused(pkg, syn, scen):
+    B = 4
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    z = syn.pose_inputs(filt, 4)["dvl"].copy()
+    z[1, 2] = np.nan
+    with pytest.raises(pkg.UwvkfError) as ei:   # host check == checkMeasurment() throwing
+        ukf.integrate_measurement(pkg.POSE_VELOCITY, z, syn.R_DVL)
+    assert ei.value.code == -4
+    Rbad = syn.R_DVL.copy(); Rbad[0, 0] = np.nan
+    with pytest.raises(pkg.UwvkfError):
+        ukf.integrate_measurement(pkg.POSE_VELOCITY, np.zeros((B, 3)), Rbad)
+    gmu, gcov = ukf.get_state()
+    assert np.array_equal(gmu, mu) and np.array_equal(gcov, cov)
+    ukf.close()
+
+
+def test_not_spd_freezes_filter(pkg, syn, scen):
+    B = 4
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    cov = cov.copy()
+    cov[2, 4, 4] = -1.0  # filter 2: negative orientation variance
+    ukf.set_state(mu, cov)
+    inp = syn.pose_inputs(filt, 1)
+    ukf.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    st = ukf.get_status()
+    assert st[2] & pkg.ST_NOT_SPD and not (np.delete(st, 2) & pkg.ST_NOT_SPD).any()
+    gmu, gcov = ukf.get_state()
+    assert np.array_equal(gmu[2], mu[2]) and np.array_equal(gcov[2], cov[2])
+    omu, ocov, st_o, _ = orc.pose_predict(mu[2], cov[2], scen["Q"], inp["gyro"][2], scen["par"], off[2], DT)
+    assert st_o & 1, "oracle flags the same filter"
+    ukf.close()
+
+
+def test_rotation_rate_getter_and_pose_reset(pkg, syn, scen):
+    B = 8
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    w = syn.pose_inputs(filt, 4)["gyro"]
+    ukf.integrate_rotation_rate(w)
+    got = ukf.get_rotation_rate()
+    ref = np.stack([orc.pose_rotation_rate(mu[f], w[f], scen["par"]) for f in range(B)])
+    assert np.abs(got - ref).max() < 1e-15
+    pose = np.tile(np.array([1.0, 2.0, 3.0, 0.0, 0.0, np.sin(0.2), np.cos(0.2)]), (B, 1))
+    ukf.reset_with_external_pose(pose)
+    mu2, cov2 = ukf.get_state()
+    assert np.array_equal(mu2[:, :7], pose) and np.array_equal(mu2[:, 7:], mu[:, 7:]) and np.array_equal(cov2, cov)
+    ukf.close()
+
+
+def test_ensemble_stats(pkg, syn, scen):
+    B = 300
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    out = ukf.ensemble_stats()
+    assert out[0] == B
+    assert np.allclose(out[1:55], mu.sum(0), rtol=1e-12, atol=1e-9)
+    M2 = mu.T @ mu
+    il = np.tril_indices(54)
+    assert np.allclose(out[55:], M2[il], rtol=1e-12, atol=1e-7)
+    ukf.close()
+
+
+def test_mean_policy_is_honoured(pkg, syn, scen):
+    """A loose tolerance stops the manifold-mean iteration earlier on both sides and the results still agree."""
+    B = 8
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    ukf.set_mean_policy(1e-3, 3)
+    w = syn.pose_inputs(filt, 1)["gyro"]
+    ukf.integrate_rotation_rate(w)
+    ukf.prediction_step(DT)
+    gmu, gcov = ukf.get_state()
+    pol = np.array([1e-3, 3.0])
+    for f in range(B):
+        omu, ocov, st, _ = orc.pose_predict(mu[f], cov[f], scen["Q"], w[f], scen["par"], off[f], DT, policy=pol)
+        assert state_err(gmu[f], omu) <= TOL_STATE and cov_err(gcov[f], ocov) <= TOL_COV
+    ukf.close()
