@@ -145,6 +145,9 @@ int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const doub
 int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int meas_kind, const double *z,
                               const double *R, int R_per_filter, const double *aux, const uint8_t *valid,
                               int memspace);
+/* Navigation solution of filters [first, first+count): out[count][10] = p(3) q(x,y,z,w) v(3) -- the leading
+ * part of getCurrentState() that a caller reads every step.  Asynchronous for memspace == UWVKF_DEVICE. */
+int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace);
 /* resetFilterWithExternalPose (src/PoseUKF.cpp:685-691): overwrite p and q of every filter, keep Sigma.
  * pose[B][7] = p(3) q(x,y,z,w), host. */
 int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose);

@@ -207,10 +207,10 @@ void pose_rotation_rate(const double *mu, const double w_meas[3], const TMerc &p
   for (int k = 0; k < 3; ++k) out[k] = w_meas[k] - mu[P_BG + k] - eb[k];
 }
 
-int pose_predict_impl(double *mu, double *cov, const double *Q, const double *w, const PoseParams &fp, const TMerc &proj,
-                      const double *offsets, double dt, const Policy &pol, int *mean_it) {
-  Ukf ukf(pose_layout(), mu, cov, pol);
-  std::vector<double> Qe;
+int pose_predict_impl(Ukf &ukf, double *mu, double *cov, const double *Q, const double *w, const PoseParams &fp, const TMerc &proj,
+                      const double *offsets, double dt, int *mean_it) {
+  ukf.reset(mu, cov);
+  static thread_local std::vector<double> Qe;
   pose_process_noise(mu, Q, fp, dt, Qe);                                                   // :448-460
   ukf.predict([&](const double *x, double *o) { pose_process_model(x, o, w, proj, offsets, fp, dt); }, Qe.data());  // :462
   if (!(ukf.status() & ST_NOT_SPD)) {
@@ -221,12 +221,12 @@ int pose_predict_impl(double *mu, double *cov, const double *Q, const double *w,
   return (int)ukf.status();
 }
 
-int pose_update_impl(int kind, double *mu, double *cov, const double *z_in, const double *R, const double *aux,
-                     const double *w_meas, const PoseParams &fp, const TMerc &proj, const Policy &pol, double *d2_out) {
+int pose_update_impl(Ukf &ukf, int kind, double *mu, double *cov, const double *z_in, const double *R, const double *aux,
+                     const double *w_meas, const PoseParams &fp, const TMerc &proj, double *d2_out) {
   int m = orc_pose_meas_dim(kind);
   if (m <= 0) return -1;
   if (has_nan(z_in, m) || has_nan(R, m * m)) return ST_NAN_MEAS;   // checkMeasurment [X4]
-  Ukf ukf(pose_layout(), mu, cov, pol);
+  ukf.reset(mu, cov);
   Layout zl = vect_layout(m);
   double z[6];
   std::memcpy(z, z_in, m * sizeof(double));
@@ -316,7 +316,8 @@ int orc_pose_predict(double *mu, double *cov, const double *Q, const double *rot
   PoseParams fp;
   std::memcpy(&fp, params, sizeof fp);
   TMerc proj(fp.lat0, fp.lon0);
-  return pose_predict_impl(mu, cov, Q, rot_rate, fp, proj, offsets, dt, make_policy(policy), mean_it);
+  Ukf ukf(pose_layout(), mu, cov, make_policy(policy));
+  return pose_predict_impl(ukf, mu, cov, Q, rot_rate, fp, proj, offsets, dt, mean_it);
 }
 
 int orc_pose_update(int kind, double *mu, double *cov, const double *z, const double *R, const double *aux,
@@ -324,7 +325,8 @@ int orc_pose_update(int kind, double *mu, double *cov, const double *z, const do
   PoseParams fp;
   std::memcpy(&fp, params, sizeof fp);
   TMerc proj(fp.lat0, fp.lon0);
-  return pose_update_impl(kind, mu, cov, z, R, aux, rot_rate, fp, proj, make_policy(policy), d2_out);
+  Ukf ukf(pose_layout(), mu, cov, make_policy(policy));
+  return pose_update_impl(ukf, kind, mu, cov, z, R, aux, rot_rate, fp, proj, d2_out);
 }
 
 void orc_pose_rotation_rate(const double *mu, const double *rot_rate, const double *params, double *out) {
@@ -440,17 +442,21 @@ double orc_pose_step_batch(int B, double *mu, double *cov, const double *Q, cons
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
   auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int f = 0; f < B; ++f) {
-    int st = 0;
-    for (int s = 0; s < nsteps; ++s) {
-      st |= pose_predict_impl(mu + (size_t)f * P_DIM, cov + (size_t)f * P_DOF * P_DOF, Q, rot_rate + (size_t)f * 3, fp, proj,
-                              offsets + (size_t)f * 28, dt, pol, nullptr);
-      if (z_vel)
-        st |= pose_update_impl(ORC_POSE_VELOCITY, mu + (size_t)f * P_DIM, cov + (size_t)f * P_DOF * P_DOF, z_vel + (size_t)f * 3,
-                               R_vel, nullptr, rot_rate + (size_t)f * 3, fp, proj, pol, nullptr);
+#pragma omp parallel
+  {
+    Ukf ukf(pose_layout(), mu, cov, pol);  // one workspace per thread
+#pragma omp for schedule(dynamic, 1)
+    for (int f = 0; f < B; ++f) {
+      int st = 0;
+      for (int s = 0; s < nsteps; ++s) {
+        st |= pose_predict_impl(ukf, mu + (size_t)f * P_DIM, cov + (size_t)f * P_DOF * P_DOF, Q, rot_rate + (size_t)f * 3, fp, proj,
+                                offsets + (size_t)f * 28, dt, nullptr);
+        if (z_vel)
+          st |= pose_update_impl(ukf, ORC_POSE_VELOCITY, mu + (size_t)f * P_DIM, cov + (size_t)f * P_DOF * P_DOF,
+                                 z_vel + (size_t)f * 3, R_vel, nullptr, rot_rate + (size_t)f * 3, fp, proj, nullptr);
+      }
+      if (status_out) status_out[f] = st;
     }
-    if (status_out) status_out[f] = st;
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();

@@ -13,6 +13,7 @@
 // Everything is executed literally (all 2n+1 points, full n x n accumulations) -- this is the CPU
 // "reference path" and the checker for the structured CUDA engine.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -97,14 +98,23 @@ class Ukf {
   using Model = std::function<void(const double *x, double *out)>;
   using Gate = std::function<bool(double)>;
 
+  // Workspaces are allocated once per object; reset() re-arms it for another filter (the batched CPU
+  // baseline keeps one object per thread so that the timed loop is free of heap traffic -- the reference's
+  // Eigen fixed-size types live on the stack, only its std::vector<state> of sigma points is heap memory).
   Ukf(const Layout &lay, const double *mu, const double *sigma, Policy pol = Policy())
-      : lay_(lay), n_(lay.dof()), dim_(lay.dim()), mu_(mu, mu + lay.dim()),
-        sigma_(sigma, sigma + lay.dof() * lay.dof()), pol_(pol) {}
+      : lay_(lay), n_(lay.dof()), dim_(lay.dim()), mu_(lay.dim()), sigma_(lay.dof() * lay.dof()), pol_(pol),
+        X_((2 * lay.dof() + 1) * lay.dim()), Y_(lay.dim()), L_(lay.dof() * lay.dof()), d_(lay.dof()), t_(lay.dof()),
+        md_(lay.dof()), ref_(lay.dim()), backup_(lay.dof() * lay.dof()), delta_(lay.dof()), Z_((2 * lay.dof() + 1) * 8) {
+    reset(mu, sigma);
+  }
+  void reset(const double *mu, const double *sigma) {
+    std::copy(mu, mu + dim_, mu_.begin());
+    std::copy(sigma, sigma + n_ * n_, sigma_.begin());
+    status_ = 0;
+  }
 
   const Vec &mu() const { return mu_; }
   const Vec &sigma() const { return sigma_; }
-  Vec &mu() { return mu_; }
-  Vec &sigma() { return sigma_; }
   int n() const { return n_; }
   unsigned status() const { return status_; }
   int last_mean_iterations() const { return last_mean_it_; }
@@ -112,126 +122,124 @@ class Ukf {
 
   // ukfom::ukf::predict(g, Q).  Returns false (state untouched) when Sigma is not SPD.
   bool predict(const Model &g, const double *Q) {
-    std::vector<Vec> X;
-    if (!sigma_points(mu_, nullptr, sigma_, X)) return false;
-    for (auto &x : X) { Vec y(dim_); g(x.data(), y.data()); x.swap(y); }
-    mu_ = mean(lay_, X);
-    sigma_ = cov(lay_, mu_, X);
+    if (!sigma_points(nullptr)) return false;
+    const int np = 2 * n_ + 1;
+    for (int i = 0; i < np; ++i) {
+      g(&X_[i * dim_], Y_.data());
+      std::copy(Y_.begin(), Y_.end(), &X_[i * dim_]);
+    }
+    mean(lay_, X_.data(), np, mu_.data());
+    cov(lay_, mu_.data(), X_.data(), np, sigma_.data());
     for (int i = 0; i < n_ * n_; ++i) sigma_[i] += Q[i];
     return true;
   }
 
-  // ukfom::ukf::update(z, h, R, mtest); zl is the manifold of the measurement.
+  // ukfom::ukf::update(z, h, R, mtest); zl is the manifold of the measurement (dim <= 8).
   // Returns true when the update was applied (gate accepted and Sigma SPD).
   bool update(const Layout &zl, const double *z, const Model &h, const double *R, const Gate &gate) {
-    const int m = zl.dof();
-    std::vector<Vec> X;
-    if (!sigma_points(mu_, nullptr, sigma_, X)) return false;
-    std::vector<Vec> Z(X.size(), Vec(zl.dim()));
-    for (size_t i = 0; i < X.size(); ++i) h(X[i].data(), Z[i].data());
-    Vec zbar = mean(zl, Z);
-    Vec S = cov(zl, zbar, Z);
+    const int m = zl.dof(), zd = zl.dim(), np = 2 * n_ + 1;
+    if (!sigma_points(nullptr)) return false;
+    for (int i = 0; i < np; ++i) h(&X_[i * dim_], &Z_[i * zd]);
+    double zbar[8], S[64], Si[64], nu[8], dz[8];
+    mean(zl, Z_.data(), np, zbar);
+    cov(zl, zbar, Z_.data(), np, S);
     for (int i = 0; i < m * m; ++i) S[i] += R[i];
     // cross_cov_sigma_points(mu_, meanZ, X, Z): deviations of X from the PRIOR mean
-    Vec Pxz(n_ * m, 0.0), dx(n_), dz(m);
-    for (size_t i = 0; i < X.size(); ++i) {
-      lay_.boxminus(X[i].data(), mu_.data(), dx.data());
-      zl.boxminus(Z[i].data(), zbar.data(), dz.data());
-      for (int a = 0; a < n_; ++a) for (int b = 0; b < m; ++b) Pxz[a * m + b] += dx[a] * dz[b];
+    Vec Pxz(n_ * m, 0.0), K(n_ * m, 0.0), KS(n_ * m, 0.0);
+    for (int i = 0; i < np; ++i) {
+      lay_.boxminus(&X_[i * dim_], mu_.data(), d_.data());
+      zl.boxminus(&Z_[i * zd], zbar, dz);
+      for (int a = 0; a < n_; ++a) for (int b = 0; b < m; ++b) Pxz[a * m + b] += d_[a] * dz[b];
     }
     for (auto &v : Pxz) v *= 0.5;
-    Vec Si(m * m);
-    small_inverse(m, S.data(), Si.data());
-    Vec K(n_ * m, 0.0);
+    small_inverse(m, S, Si);
     for (int a = 0; a < n_; ++a) for (int b = 0; b < m; ++b) {
       double s = 0; for (int c = 0; c < m; ++c) s += Pxz[a * m + c] * Si[c * m + b];
       K[a * m + b] = s;
     }
-    Vec nu(m);
-    zl.boxminus(z, zbar.data(), nu.data());
+    zl.boxminus(z, zbar, nu);
     double d2 = 0;
     for (int a = 0; a < m; ++a) for (int b = 0; b < m; ++b) d2 += nu[a] * Si[a * m + b] * nu[b];
     last_d2_ = d2;
     if (!gate(d2)) { status_ |= ST_GATE_REJECTED; return false; }
     // sigma_ -= K * S * K^T  (evaluated as (K*S)*K^T over the full matrix, like Eigen)
-    Vec KS(n_ * m, 0.0);
     for (int a = 0; a < n_; ++a) for (int b = 0; b < m; ++b) {
       double s = 0; for (int c = 0; c < m; ++c) s += K[a * m + c] * S[c * m + b];
       KS[a * m + b] = s;
     }
-    Vec sig_backup = sigma_;
+    backup_ = sigma_;
     for (int a = 0; a < n_; ++a) for (int b = 0; b < n_; ++b) {
       double s = 0; for (int c = 0; c < m; ++c) s += KS[a * m + c] * K[b * m + c];
       sigma_[a * n_ + b] -= s;
     }
-    Vec delta(n_, 0.0);
-    for (int a = 0; a < n_; ++a) { double s = 0; for (int c = 0; c < m; ++c) s += K[a * m + c] * nu[c]; delta[a] = s; }
-    if (!apply_delta(delta)) { sigma_ = sig_backup; return false; }
+    for (int a = 0; a < n_; ++a) { double s = 0; for (int c = 0; c < m; ++c) s += K[a * m + c] * nu[c]; delta_[a] = s; }
+    if (!apply_delta(delta_.data())) { sigma_ = backup_; return false; }
     return true;
   }
 
   // ukfom::ukf::apply_delta(delta)
-  bool apply_delta(const Vec &delta) {
-    std::vector<Vec> X;
-    if (!sigma_points(mu_, delta.data(), sigma_, X)) return false;
-    mu_ = mean(lay_, X);
-    sigma_ = cov(lay_, mu_, X);
+  bool apply_delta(const double *delta) {
+    if (!sigma_points(delta)) return false;
+    const int np = 2 * n_ + 1;
+    mean(lay_, X_.data(), np, mu_.data());
+    cov(lay_, mu_.data(), X_.data(), np, sigma_.data());
     return true;
   }
 
  private:
-  bool sigma_points(const Vec &mu, const double *delta, const Vec &sigma, std::vector<Vec> &X) {
-    Vec L(n_ * n_);
-    if (!cholesky_lower(n_, sigma.data(), L.data())) { status_ |= ST_NOT_SPD; return false; }
-    X.assign(2 * n_ + 1, Vec(dim_));
-    Vec d(n_, 0.0);
-    if (delta) d.assign(delta, delta + n_);
-    lay_.boxplus(mu.data(), d.data(), 1.0, X[0].data());
-    Vec t(n_);
+  // generate_sigma_points(mu_, delta, sigma_, X)
+  bool sigma_points(const double *delta) {
+    if (!cholesky_lower(n_, sigma_.data(), L_.data())) { status_ |= ST_NOT_SPD; return false; }
+    for (int a = 0; a < n_; ++a) d_[a] = delta ? delta[a] : 0.0;
+    lay_.boxplus(mu_.data(), d_.data(), 1.0, &X_[0]);
     for (int j = 0, i = 1; j < n_; ++j) {
-      for (int a = 0; a < n_; ++a) t[a] = d[a] + L[a * n_ + j];
-      lay_.boxplus(mu.data(), t.data(), 1.0, X[i++].data());
-      for (int a = 0; a < n_; ++a) t[a] = d[a] - L[a * n_ + j];
-      lay_.boxplus(mu.data(), t.data(), 1.0, X[i++].data());
+      for (int a = 0; a < n_; ++a) t_[a] = d_[a] + L_[a * n_ + j];
+      lay_.boxplus(mu_.data(), t_.data(), 1.0, &X_[(i++) * dim_]);
+      for (int a = 0; a < n_; ++a) t_[a] = d_[a] - L_[a * n_ + j];
+      lay_.boxplus(mu_.data(), t_.data(), 1.0, &X_[(i++) * dim_]);
     }
     return true;
   }
 
-  Vec mean(const Layout &l, const std::vector<Vec> &X) {
-    const int nd = l.dof();
-    Vec ref = X[0], md(nd), d(nd);
+  // mean_sigma_points: X holds np points of l.dim() doubles; out may alias nothing in X
+  void mean(const Layout &l, const double *X, int np, double *out) {
+    const int nd = l.dof(), dm = l.dim();
+    double *ref = ref_.data(), *md = md_.data(), *d = t_.data();
+    std::copy(X, X + dm, ref);
     int it = 0;
     double nrm;
     do {
-      for (auto &v : md) v = 0;
-      for (auto &x : X) {
-        l.boxminus(x.data(), ref.data(), d.data());
+      for (int a = 0; a < nd; ++a) md[a] = 0;
+      for (int i = 0; i < np; ++i) {
+        l.boxminus(X + i * dm, ref, d);
         for (int a = 0; a < nd; ++a) md[a] += d[a];
       }
-      for (auto &v : md) v /= (double)X.size();
-      l.boxplus(ref.data(), md.data(), 1.0, ref.data());
-      nrm = 0; for (auto v : md) nrm += v * v; nrm = std::sqrt(nrm);
+      for (int a = 0; a < nd; ++a) md[a] /= (double)np;
+      l.boxplus(ref, md, 1.0, ref);
+      nrm = 0; for (int a = 0; a < nd; ++a) nrm += md[a] * md[a]; nrm = std::sqrt(nrm);
     } while (nrm > pol_.mean_tol && ++it < pol_.mean_max_it);
     last_mean_it_ = it + 1;
     if (it >= pol_.mean_max_it) status_ |= ST_MEAN_NOT_CONVERGED;
-    return ref;
+    std::copy(ref, ref + dm, out);
   }
 
-  Vec cov(const Layout &l, const Vec &mean, const std::vector<Vec> &X) {
-    const int nd = l.dof();
-    Vec c(nd * nd, 0.0), d(nd);
-    for (auto &x : X) {
-      l.boxminus(x.data(), mean.data(), d.data());
+  // cov_sigma_points: c = 1/2 sum d d^T over all points (full matrix)
+  void cov(const Layout &l, const double *mean, const double *X, int np, double *c) {
+    const int nd = l.dof(), dm = l.dim();
+    double *d = t_.data();
+    for (int i = 0; i < nd * nd; ++i) c[i] = 0.0;
+    for (int i = 0; i < np; ++i) {
+      l.boxminus(X + i * dm, mean, d);
       for (int a = 0; a < nd; ++a) { double da = d[a]; double *row = &c[a * nd]; for (int b = 0; b < nd; ++b) row[b] += da * d[b]; }
     }
-    for (auto &v : c) v *= 0.5;
-    return c;
+    for (int i = 0; i < nd * nd; ++i) c[i] *= 0.5;
   }
 
   Layout lay_;
   int n_, dim_;
   Vec mu_, sigma_;
   Policy pol_;
+  Vec X_, Y_, L_, d_, t_, md_, ref_, backup_, delta_, Z_;
   unsigned status_ = 0;
   int last_mean_it_ = 0;
   double last_d2_ = 0;

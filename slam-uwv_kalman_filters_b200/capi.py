@@ -63,6 +63,7 @@ def load_library():
         lib.uwvkf_pose_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_pose_predict_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
@@ -168,6 +169,17 @@ class PoseUKFBatch:
     def get_state_into(self, mu, cov=None, first=0, count=None, memspace=HOST):
         count = self.batch - first if count is None else count
         self._ck(self._lib.uwvkf_get_state(self._h, _ptr(mu), _ptr(cov), first, count, memspace))
+
+    def get_navigation(self, first=0, count=None):
+        """p(3), q(x,y,z,w), v(3) of every filter: the part of getCurrentState() read every step."""
+        count = self.batch - first if count is None else count
+        out = np.empty((count, 10))
+        self._ck(self._lib.uwvkf_pose_get_navigation(self._h, _ptr(out), first, count, HOST))
+        return out
+
+    def get_navigation_into(self, out, first=0, count=None, memspace=HOST):
+        count = self.batch - first if count is None else count
+        self._ck(self._lib.uwvkf_pose_get_navigation(self._h, _ptr(out), first, count, memspace))
 
     def get_status(self, first=0, count=None):
         count = self.batch - first if count is None else count

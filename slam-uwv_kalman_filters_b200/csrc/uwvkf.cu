@@ -141,6 +141,10 @@ __global__ void pose_unpack_kernel(const double *state, double *mu, double *cov,
     }
   }
 }
+__global__ void pose_get_nav_kernel(const double *state, double *out, long long first, long long count) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < count * 10) { long long f = g / 10; int k = (int)(g - f * 10); out[g] = state[(first + f) * pose::BLK + k]; }
+}
 __global__ void pose_set_pose_kernel(double *state, const double *pose7, long long B) {
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < B * 7) { long long f = g / 7; int k = (int)(g - f * 7); state[f * pose::BLK + k] = pose7[g]; }
@@ -598,6 +602,25 @@ int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int me
   int rc = make_update_op(h, meas_kind, z, R, R_per_filter, aux, valid, memspace, ops[1]);
   if (rc) return rc;
   return run_pose(h, 2, ops);
+}
+
+int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!out || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  double *dout = out;
+  if (memspace == UWVKF_HOST) {
+    int rc = ensure_tmp(h, (size_t)count * 10 * sizeof(double));
+    if (rc) return rc;
+    dout = h->d_tmp;
+  }
+  pose_get_nav_kernel<<<(unsigned)((count * 10 + 255) / 256), 256, 0, h->stream>>>(h->d_state, dout, first, count);
+  CK(cudaGetLastError());
+  h->launches++;
+  if (memspace == UWVKF_HOST) {
+    CK(cudaMemcpyAsync(out, dout, (size_t)count * 10 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return UWVKF_OK;
 }
 
 int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose7) {

@@ -204,7 +204,7 @@ R_PRESSURE = np.array([[1e4]])
 R_ADCP = 4e-4 * np.eye(2)
 
 
-def pose_initial_batch(filters, cfg=None, spread=1.0):
+def pose_initial_batch(filters, cfg=None, spread=1.0, with_cov=True):
     """Per-filter initial states: mu0 (+) L0*eps with independent draws (Monte-Carlo ensemble). Returns (mu[B,54], cov[B,53,53])."""
     if cfg is None:
         cfg = pose_config()
@@ -226,5 +226,5 @@ def pose_initial_batch(filters, cfg=None, spread=1.0):
     sc = np.where(ang > 1e-12, np.sin(half) / np.maximum(ang, 1e-300), 0.5)
     mu[:, 3:6] = v * sc[:, None]
     mu[:, 6] = np.cos(half)
-    cov = np.tile(cov0, (B, 1, 1))
+    cov = np.tile(cov0, (B, 1, 1)) if with_cov else cov0
     return mu, cov
