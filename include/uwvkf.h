@@ -152,8 +152,52 @@ int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_
  * pose[B][7] = p(3) q(x,y,z,w), host. */
 int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose);
 
+/* ---- VelocityUKF (src/VelocityUKF.hpp:33-66) ------------------------------------------------------------ */
+enum uwvkf_velocity_meas {
+  UWVKF_VEL_DVL = 0,      /* DVLMeasurement m=3       src/VelocityUKF.cpp:79-85 */
+  UWVKF_VEL_PRESSURE = 1  /* PressureMeasurement m=1  src/VelocityUKF.cpp:106-112 */
+};
+/* flat uwv_dynamic_model::UWVParameters: inertia 6x6, linear damping 6x6, quadratic damping 6x6 (row-major),
+ * distance_body2centerofgravity[3], distance_body2centerofbuoyancy[3], weight, buoyancy */
+#define UWVKF_UWV_NPARAMS 116
+/* setupMotionModel(parameters) (src/VelocityUKF.cpp:58-77); uwvkf_predict fails with UWVKF_ERR_NOT_INITIALIZED
+ * ("Motion model is not initialized!", :117-118) until this was called. */
+int uwvkf_velocity_setup_motion_model(uwvkf_handle h, const double *uwv_params);
+/* integrateMeasurement(GyroMeasurement) (:87-98): w[B][3] */
+int uwvkf_velocity_set_gyro(uwvkf_handle h, const double *w, int memspace);
+/* integrateMeasurement(BodyEffortsMeasurement) (:100-104): tau[B][6] */
+int uwvkf_velocity_set_efforts(uwvkf_handle h, const double *tau, int memspace);
+/* integrateMeasurement(DVLMeasurement / PressureMeasurement): z[B][m], R[m*m] shared */
+int uwvkf_velocity_update(uwvkf_handle h, int meas_kind, const double *z, const double *R, const uint8_t *valid, int memspace);
+/* state of the private motion model (src/VelocityUKF.hpp:62): sim[B][10] = q(x,y,z,w), linear(3), angular(3) velocity */
+int uwvkf_velocity_get_motion_model_state(uwvkf_handle h, double *sim);
+
+/* ---- BottomUKF (src/BottomUKF.hpp:27-52) ---------------------------------------------------------------- */
+/* setVelocity (src/BottomUKF.cpp:69-72): v[B][3] */
+int uwvkf_bottom_set_velocity(uwvkf_handle h, const double *v, int memspace);
+/* integrateMeasurement(RangeMeasurement, unit_direction, origin) (:56-61): z[B], R[1], beam geometry shared */
+int uwvkf_bottom_update_range(uwvkf_handle h, const double *z, const double *R, const double *unit_direction,
+                              const double *origin, const uint8_t *valid, int memspace);
+/* integrateMeasurement(NormalType, measurement_cov) (:63-67): z[B][3] unit vectors, R[2*2] */
+int uwvkf_bottom_update_normal(uwvkf_handle h, const double *z, const double *R, const uint8_t *valid, int memspace);
+
+/* ---- IndirectPoseUKF (src/IndirectPoseUKF.hpp:29-85) ---------------------------------------------------- */
+/* orientation_error_tau of the constructor (src/IndirectPoseUKF.cpp:53-58); the initial state / covariance /
+ * process noise the constructor derives (:60-77) are set with uwvkf_set_state / uwvkf_set_process_noise */
+int uwvkf_indirect_set_tau(uwvkf_handle h, double orientation_error_tau);
+/* updatePoseReference (:144-147): pose_ref[B][7] = t(3) q(x,y,z,w), body in world */
+int uwvkf_indirect_update_pose_reference(uwvkf_handle h, const double *pose_ref, int memspace);
+/* integrateMeasurement(marker_features, feature_positions, marker_pose, cov_marker_pose, camera_config,
+ * camera_in_body) (:94-135): px[B][nfeat][2] pixel coordinates, pxcov[nfeat][4], feature_pos[nfeat][3],
+ * marker_pose[7], cov_marker[36], camera = fx, fy, cx, cy, cam_in_body[7]; 1 <= nfeat <= 8 */
+int uwvkf_indirect_update_features(uwvkf_handle h, int nfeat, const double *px, const double *pxcov,
+                                   const double *feature_pos, const double *marker_pose, const double *cov_marker,
+                                   const double *camera, const double *cam_in_body, const uint8_t *valid, int memspace);
+/* getCorrectedPose (:137-142): out[B][7], host */
+int uwvkf_indirect_get_corrected_pose(uwvkf_handle h, double *out);
+
 /* ---- ensemble statistics (north_star: the only cross-GPU exchange) -------------------------------- */
-/* Writes [count, sum mu (DIM), sum mu mu^T lower-packed (DIM*(DIM+1)/2)] over this handle's filters into
+/* Writes [count, sum mu (DIM), sum mu mu^T lower triangle row-major (DIM*(DIM+1)/2)] over this handle's filters into
  * out (device or host pointer, 1 + DIM + DIM*(DIM+1)/2 doubles).  The caller all-reduces it (NCCL sum). */
 int uwvkf_ensemble_stats(uwvkf_handle h, double *out, int memspace);
 int64_t uwvkf_ensemble_stats_size(uwvkf_handle h);

@@ -61,6 +61,26 @@ double orc_pose_step_batch(int B, double *mu, double *cov, const double *Q, cons
                            int nthreads, const double *policy, int *status_out);
 int orc_num_threads(void);
 
+/* VelocityUKF (src/VelocityUKF.cpp). mu[4], cov[16]; sim[10] = q(x,y,z,w), linear(3), angular(3) of the private motion
+ * model; uwv[116] = inertia 6x6, lin damping 6x6, quad damping 6x6 (row-major), cog[3], cob[3], weight, buoyancy */
+#define ORC_UWV_N 116
+void orc_vel_setup_motion_model(const double *mu, const double *gyro, double *sim);
+int orc_vel_predict(double *mu, double *cov, const double *Q, double *sim, const double *gyro, const double *efforts,
+                    const double *uwv, double dt, const double *policy);
+int orc_vel_update(int kind /*0 DVL (3), 1 pressure (1)*/, double *mu, double *cov, const double *z, const double *R,
+                   const double *policy);
+/* BottomUKF (src/BottomUKF.cpp). mu[4] = distance, normal(3); cov[9] */
+int orc_bottom_predict(double *mu, double *cov, const double *Q, const double *velocity, double dt, const double *policy);
+int orc_bottom_update_range(double *mu, double *cov, const double *z, const double *R, const double *unit_direction,
+                            const double *origin, const double *policy);
+int orc_bottom_update_normal(double *mu, double *cov, const double *z, const double *R, const double *policy);
+/* IndirectPoseUKF (src/IndirectPoseUKF.cpp). mu[7] = position_error, q(x,y,z,w); cov[36]; poses = t[3], q[4] */
+int orc_indirect_predict(double *mu, double *cov, const double *Q, double tau, double dt, const double *policy);
+int orc_indirect_update_features(double *mu, double *cov, int nfeat, const double *px, const double *pxcov,
+                                 const double *feature_pos, const double *marker_pose, const double *cov_marker,
+                                 const double *camera, const double *cam_in_body, const double *pose_ref, const double *policy);
+void orc_indirect_corrected_pose(const double *mu, const double *pose_ref, double *out);
+
 void orc_tmerc_world_to_nav(double lat0, double lon0, double lat, double lon, double *xy);
 void orc_tmerc_nav_to_world(double lat0, double lon0, double x, double y, double *latlon);
 double orc_gravity_wgs84(double lat, double alt);

@@ -66,6 +66,19 @@ def load_library():
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        vp, ci = C.c_void_p, C.c_int
+        lib.uwvkf_velocity_setup_motion_model.argtypes = [vp, vp]
+        lib.uwvkf_velocity_set_gyro.argtypes = [vp, vp, ci]
+        lib.uwvkf_velocity_set_efforts.argtypes = [vp, vp, ci]
+        lib.uwvkf_velocity_update.argtypes = [vp, ci, vp, vp, vp, ci]
+        lib.uwvkf_velocity_get_motion_model_state.argtypes = [vp, vp]
+        lib.uwvkf_bottom_set_velocity.argtypes = [vp, vp, ci]
+        lib.uwvkf_bottom_update_range.argtypes = [vp, vp, vp, vp, vp, vp, ci]
+        lib.uwvkf_bottom_update_normal.argtypes = [vp, vp, vp, vp, ci]
+        lib.uwvkf_indirect_set_tau.argtypes = [vp, C.c_double]
+        lib.uwvkf_indirect_update_pose_reference.argtypes = [vp, vp, ci]
+        lib.uwvkf_indirect_update_features.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, ci]
+        lib.uwvkf_indirect_get_corrected_pose.argtypes = [vp, vp]
         _lib = lib
     return _lib
 
@@ -86,27 +99,24 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-class PoseUKFBatch:
-    """A batch of independent uwv_kalman_filters::PoseUKF instances on one GPU.
+def _u8(valid):
+    if valid is None or isinstance(valid, int):
+        return valid
+    return np.ascontiguousarray(valid, dtype=np.uint8)
 
-    Mirrors the reference class (src/PoseUKF.hpp:40-208): the second constructor (state, covariance,
-    location, parameters; :113-115), predictionStep(dt), integrateMeasurement(<typed measurement>), and the
-    getters.  Batch = 1 behaves like one reference object.  Array arguments are numpy arrays (host) or raw
-    integer device pointers with memspace=DEVICE.
-    """
 
-    DIM, DOF = 54, 53
+class _FilterBatch:
+    """Common part of the batched filter mirrors: handle lifetime, state access, status, ensemble statistics."""
+    KIND, DIM, DOF = None, 0, 0
 
-    def __init__(self, batch, params, device=0, stream=None):
+    def __init__(self, batch, device=0, stream=None):
         self._lib = load_library()
         self._h = C.c_void_p()
         self.batch = int(batch)
-        self._ck(self._lib.uwvkf_create(FILTER_POSE, self.batch, device, C.byref(self._h)))
+        self._ck(self._lib.uwvkf_create(self.KIND, self.batch, device, C.byref(self._h)))
         if stream is not None:
             self._ck(self._lib.uwvkf_set_stream(self._h, C.c_void_p(stream)))
-        self.set_params(params)
 
-    # -- plumbing
     def _ck(self, rc):
         if rc != 0:
             raise UwvkfError(rc, self._lib.uwvkf_last_error().decode())
@@ -129,40 +139,27 @@ class PoseUKFBatch:
     def kernel_launches(self):
         return int(self._lib.uwvkf_kernel_launches(self._h))
 
-    # -- configuration
-    def set_params(self, params):
-        p = _f64(params)
-        assert p.shape == (22,)
-        self._ck(self._lib.uwvkf_pose_set_params(self._h, _ptr(p)))
-
     def set_mean_policy(self, tol, max_it):
         self._ck(self._lib.uwvkf_set_mean_policy(self._h, float(tol), int(max_it)))
 
     def set_process_noise(self, Q):
-        """setProcessNoiseCovariance (reference src/PoseUKF.cpp:438)."""
+        """setProcessNoiseCovariance of the reference base class."""
         Q = _f64(Q)
-        assert Q.shape == (53, 53)
+        assert Q.shape == (self.DOF, self.DOF)
         self._ck(self._lib.uwvkf_set_process_noise(self._h, _ptr(Q)))
 
     def set_state(self, mu, cov, first=0, memspace=HOST, count=None):
-        """initializeFilter(state, cov); cov is [count,53,53] or a single shared [53,53]."""
+        """initializeFilter(state, cov); cov is [count,DOF,DOF] or a single shared [DOF,DOF]."""
         mu, cov = _f64(mu), _f64(cov)
         if count is None:
             count = mu.shape[0]
-        stride = 0
-        if isinstance(cov, int) or cov.ndim == 3:
-            stride = 53 * 53
+        stride = self.DOF * self.DOF if (isinstance(cov, int) or cov.ndim == 3) else 0
         self._ck(self._lib.uwvkf_set_state(self._h, _ptr(mu), _ptr(cov), stride, first, count, memspace))
 
-    def set_offsets(self, offsets, first=0):
-        o = _f64(offsets)
-        self._ck(self._lib.uwvkf_pose_set_offsets(self._h, _ptr(o), first, o.shape[0]))
-
-    # -- getters
     def get_state(self, first=0, count=None, with_cov=True):
         count = self.batch - first if count is None else count
-        mu = np.empty((count, 54))
-        cov = np.empty((count, 53, 53)) if with_cov else None
+        mu = np.empty((count, self.DIM))
+        cov = np.empty((count, self.DOF, self.DOF)) if with_cov else None
         self._ck(self._lib.uwvkf_get_state(self._h, _ptr(mu), _ptr(cov), first, count, HOST))
         return (mu, cov) if with_cov else mu
 
@@ -170,6 +167,130 @@ class PoseUKFBatch:
         count = self.batch - first if count is None else count
         self._ck(self._lib.uwvkf_get_state(self._h, _ptr(mu), _ptr(cov), first, count, memspace))
 
+    def get_status(self, first=0, count=None):
+        count = self.batch - first if count is None else count
+        st = np.empty(count, dtype=np.uint32)
+        self._ck(self._lib.uwvkf_get_status(self._h, _ptr(st), first, count))
+        return st
+
+    def clear_status(self):
+        self._ck(self._lib.uwvkf_clear_status(self._h))
+
+    def prediction_step(self, dt):
+        """predictionStep(dt) of the reference base class -> predictionStepImpl of the filter."""
+        self._ck(self._lib.uwvkf_predict(self._h, float(dt)))
+
+    def ensemble_stats_size(self):
+        return int(self._lib.uwvkf_ensemble_stats_size(self._h))
+
+    def ensemble_stats(self, out=None, memspace=HOST):
+        """[count, sum mu, sum mu mu^T (lower, row-major)] over this rank's filters; all-reduce (sum) across ranks."""
+        if out is None:
+            out = np.empty(self.ensemble_stats_size())
+        self._ck(self._lib.uwvkf_ensemble_stats(self._h, _ptr(out), memspace))
+        return out
+
+
+class VelocityUKFBatch(_FilterBatch):
+    """Batch of uwv_kalman_filters::VelocityUKF (reference src/VelocityUKF.hpp:33-66)."""
+    KIND, DIM, DOF = FILTER_VELOCITY, 4, 4
+    DVL, PRESSURE = 0, 1
+
+    def setup_motion_model(self, uwv_params):
+        """setupMotionModel(parameters) (src/VelocityUKF.cpp:58-77); uwv_params: flat UWVParameters (116)."""
+        p = _f64(uwv_params)
+        assert p.shape == (116,)
+        self._ck(self._lib.uwvkf_velocity_setup_motion_model(self._h, _ptr(p)))
+
+    def integrate_gyro(self, w, memspace=HOST):
+        self._ck(self._lib.uwvkf_velocity_set_gyro(self._h, _ptr(_f64(w)), memspace))
+
+    def integrate_body_efforts(self, tau, memspace=HOST):
+        self._ck(self._lib.uwvkf_velocity_set_efforts(self._h, _ptr(_f64(tau)), memspace))
+
+    def integrate_measurement(self, kind, z, R, valid=None, memspace=HOST):
+        self._ck(self._lib.uwvkf_velocity_update(self._h, kind, _ptr(_f64(z)), _ptr(_f64(R)), _ptr(_u8(valid)), memspace))
+
+    def get_motion_model_state(self):
+        out = np.empty((self.batch, 10))
+        self._ck(self._lib.uwvkf_velocity_get_motion_model_state(self._h, _ptr(out)))
+        return out
+
+
+class BottomUKFBatch(_FilterBatch):
+    """Batch of uwv_kalman_filters::BottomUKF (reference src/BottomUKF.hpp:27-52)."""
+    KIND, DIM, DOF = FILTER_BOTTOM, 4, 3
+
+    def set_velocity(self, v, memspace=HOST):
+        self._ck(self._lib.uwvkf_bottom_set_velocity(self._h, _ptr(_f64(v)), memspace))
+
+    def integrate_range(self, z, R, unit_direction, origin, valid=None, memspace=HOST):
+        self._ck(self._lib.uwvkf_bottom_update_range(self._h, _ptr(_f64(z)), _ptr(_f64(np.atleast_1d(R))), _ptr(_f64(unit_direction)),
+                                                     _ptr(_f64(origin)), _ptr(_u8(valid)), memspace))
+
+    def integrate_normal(self, z, R, valid=None, memspace=HOST):
+        self._ck(self._lib.uwvkf_bottom_update_normal(self._h, _ptr(_f64(z)), _ptr(_f64(R)), _ptr(_u8(valid)), memspace))
+
+
+class IndirectPoseUKFBatch(_FilterBatch):
+    """Batch of uwv_kalman_filters::IndirectPoseUKF (reference src/IndirectPoseUKF.hpp:29-85)."""
+    KIND, DIM, DOF = FILTER_INDIRECT_POSE, 7, 6
+
+    def __init__(self, batch, position_error_std, orientation_error_std, orientation_error_tau,
+                 initial_position_error=(0.0, 0.0, 0.0), initial_position_error_std=(1.0, 1.0, 1.0), device=0, stream=None):
+        """Mirrors the constructor (src/IndirectPoseUKF.cpp:53-78): state, covariance and process noise from the stds."""
+        super().__init__(batch, device, stream)
+        pes, oes = np.asarray(position_error_std, float), np.asarray(orientation_error_std, float)
+        mu = np.zeros(7)
+        mu[0:3] = initial_position_error
+        mu[6] = 1.0
+        cov = np.diag(np.concatenate([np.asarray(initial_position_error_std, float) ** 2, oes ** 2]))
+        self.set_state(np.tile(mu, (self.batch, 1)), cov)
+        self.set_process_noise(np.diag(np.concatenate([pes ** 2, oes ** 2])))
+        self._ck(self._lib.uwvkf_indirect_set_tau(self._h, float(orientation_error_tau)))
+
+    def update_pose_reference(self, pose_ref, memspace=HOST):
+        self._ck(self._lib.uwvkf_indirect_update_pose_reference(self._h, _ptr(_f64(pose_ref)), memspace))
+
+    def integrate_features(self, px, pxcov, feature_pos, marker_pose, cov_marker, camera, cam_in_body, valid=None, memspace=HOST):
+        """integrateMeasurement(marker_features, ...) (src/IndirectPoseUKF.cpp:94-135); px: [B, nfeat, 2]."""
+        px = _f64(px)
+        nfeat = np.asarray(feature_pos).shape[0]
+        self._ck(self._lib.uwvkf_indirect_update_features(self._h, nfeat, _ptr(px), _ptr(_f64(pxcov)), _ptr(_f64(feature_pos)),
+                                                          _ptr(_f64(marker_pose)), _ptr(_f64(cov_marker)), _ptr(_f64(camera)),
+                                                          _ptr(_f64(cam_in_body)), _ptr(_u8(valid)), memspace))
+
+    def get_corrected_pose(self):
+        out = np.empty((self.batch, 7))
+        self._ck(self._lib.uwvkf_indirect_get_corrected_pose(self._h, _ptr(out)))
+        return out
+
+
+class PoseUKFBatch(_FilterBatch):
+    """A batch of independent uwv_kalman_filters::PoseUKF instances on one GPU.
+
+    Mirrors the reference class (src/PoseUKF.hpp:40-208): the second constructor (state, covariance,
+    location, parameters; :113-115), predictionStep(dt), integrateMeasurement(<typed measurement>), and the
+    getters.  Batch = 1 behaves like one reference object.  Array arguments are numpy arrays (host) or raw
+    integer device pointers with memspace=DEVICE.
+    """
+
+    KIND, DIM, DOF = FILTER_POSE, 54, 53
+
+    def __init__(self, batch, params, device=0, stream=None):
+        super().__init__(batch, device, stream)
+        self.set_params(params)
+
+    def set_params(self, params):
+        p = _f64(params)
+        assert p.shape == (22,)
+        self._ck(self._lib.uwvkf_pose_set_params(self._h, _ptr(p)))
+
+    def set_offsets(self, offsets, first=0):
+        o = _f64(offsets)
+        self._ck(self._lib.uwvkf_pose_set_offsets(self._h, _ptr(o), first, o.shape[0]))
+
+    # -- getters
     def get_navigation(self, first=0, count=None):
         """p(3), q(x,y,z,w), v(3) of every filter: the part of getCurrentState() read every step."""
         count = self.batch - first if count is None else count
@@ -181,15 +302,6 @@ class PoseUKFBatch:
         count = self.batch - first if count is None else count
         self._ck(self._lib.uwvkf_pose_get_navigation(self._h, _ptr(out), first, count, memspace))
 
-    def get_status(self, first=0, count=None):
-        count = self.batch - first if count is None else count
-        st = np.empty(count, dtype=np.uint32)
-        self._ck(self._lib.uwvkf_get_status(self._h, _ptr(st), first, count))
-        return st
-
-    def clear_status(self):
-        self._ck(self._lib.uwvkf_clear_status(self._h))
-
     def get_rotation_rate(self):
         """getRotationRate() (reference src/PoseUKF.cpp:693-699) for every filter."""
         out = np.empty((self.batch, 3))
@@ -200,10 +312,6 @@ class PoseUKFBatch:
     def integrate_rotation_rate(self, w, memspace=HOST):
         """integrateMeasurement(const RotationRate&) (src/PoseUKF.cpp:492-496)."""
         self._ck(self._lib.uwvkf_pose_set_rotation_rate(self._h, _ptr(_f64(w)), memspace))
-
-    def prediction_step(self, dt):
-        """predictionStep(dt) (src/PoseUKF.cpp:446-466)."""
-        self._ck(self._lib.uwvkf_predict(self._h, float(dt)))
 
     def integrate_measurement(self, kind, z, R, aux=None, valid=None, memspace=HOST):
         """integrateMeasurement(<kind>) (src/PoseUKF.cpp:476-611). R: [m,m] shared or [B,m,m]."""
@@ -225,13 +333,3 @@ class PoseUKFBatch:
     def reset_with_external_pose(self, pose7):
         """resetFilterWithExternalPose (src/PoseUKF.cpp:685-691)."""
         self._ck(self._lib.uwvkf_pose_reset_with_external_pose(self._h, _ptr(_f64(pose7))))
-
-    def ensemble_stats_size(self):
-        return int(self._lib.uwvkf_ensemble_stats_size(self._h))
-
-    def ensemble_stats(self, out=None, memspace=HOST):
-        """[count, sum mu, sum mu mu^T (lower packed)] over this rank's filters; all-reduce (sum) across ranks."""
-        if out is None:
-            out = np.empty(self.ensemble_stats_size())
-        self._ck(self._lib.uwvkf_ensemble_stats(self._h, _ptr(out), memspace))
-        return out

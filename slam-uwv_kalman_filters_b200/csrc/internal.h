@@ -1,0 +1,69 @@
+// Internal declarations shared by the translation units of libuwvkf.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/uwvkf.h"
+#include "pose_engine.cuh"
+#include "small_engine.cuh"
+
+namespace uwvkf {
+int fail(int code, const std::string &msg);
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return uwvkf::fail(UWVKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+struct uwvkf_filter_s {
+  int kind = 0;
+  int64_t B = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  uint32_t *d_status = nullptr;
+  double mean_tol = 1e-9;
+  int mean_max_it = 100;
+  // staging for host inputs
+  double *d_z = nullptr, *d_Rpf = nullptr;
+  uint8_t *d_valid = nullptr;
+  double *d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  // PoseUKF
+  double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr;
+  uwvkf::pose::Params pp{};
+  bool have_params = false, have_Q = false;
+  // small filters: state[B][dim + dof*dof], controls, shared process noise
+  int dim = 0, dof = 0;
+  double Qh[36] = {0};
+  double *d_ctrl0 = nullptr, *d_ctrl1 = nullptr, *d_sim = nullptr;  // velocity: gyro, efforts, simulator; bottom: velocity; indirect: pose_ref
+  uwvkf::small::UwvParams uwv{};
+  bool have_model = false;
+  double tau = 0.0;
+};
+
+namespace uwvkf {
+int ensure_tmp(uwvkf_handle h, size_t bytes);
+int stage(uwvkf_handle h, const void *src, size_t bytes, size_t cap, int memspace, void **slot, const void **out);
+// small filters (small_filters.cu)
+int small_create(uwvkf_handle h);
+void small_destroy(uwvkf_handle h);
+int small_set_state(uwvkf_handle h, const double *mu, const double *cov, int64_t cov_stride, int64_t first, int64_t count, int memspace);
+int small_get_state(uwvkf_handle h, double *mu, double *cov, int64_t first, int64_t count, int memspace);
+int small_predict(uwvkf_handle h, double dt);
+int small_ensemble_stats(uwvkf_handle h, double *dout);
+}  // namespace uwvkf
+
+#define REQUIRE(h, k)                                                                                             \
+  if (!(h)) return uwvkf::fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");                                        \
+  if ((h)->kind != (k)) return uwvkf::fail(UWVKF_ERR_INVALID_ARGUMENT, "wrong filter kind for this call");       \
+  CK(cudaSetDevice((h)->device));

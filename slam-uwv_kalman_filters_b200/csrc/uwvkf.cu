@@ -1,27 +1,14 @@
 // uwvkf C ABI (include/uwvkf.h) + kernel launchers.  Thin host code over the CUDA kernels; no CPU path.
-#include <cuda_runtime.h>
+#include "internal.h"
 
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/uwvkf.h"
-#include "pose_engine.cuh"
+namespace uwvkf {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+}  // namespace uwvkf
 
 namespace {
 
 using namespace uwvkf;
-
-thread_local std::string g_err;
-int fail(int code, const std::string &msg) { g_err = msg; return code; }
-#define CK(call)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e_ = (call);                                                                          \
-    if (e_ != cudaSuccess)                                                                            \
-      return fail(UWVKF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
-  } while (0)
 
 __device__ uint16_t g_lut[pose::NP];  // packed index -> (row | col << 8)
 
@@ -202,30 +189,24 @@ __global__ void ensemble_stats_kernel(const double *state, long long stride, lon
 
 }  // namespace
 
-// ======================================================================================================
-struct uwvkf_filter_s {
-  int kind = 0;
-  int64_t B = 0;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  int sm_count = 148;
-  int64_t launches = 0;
-  // PoseUKF
-  double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr;
-  uint32_t *d_status = nullptr;
-  double *d_z = nullptr, *d_Rpf = nullptr, *d_w = nullptr;  // staging for host inputs
-  uint8_t *d_valid = nullptr;
-  double *d_tmp = nullptr;
-  size_t tmp_bytes = 0;
-  pose::Params pp{};
-  bool have_params = false, have_Q = false;
-};
+namespace uwvkf {
+int small_ensemble_stats(uwvkf_handle h, double *dout) {
+  int grid = (int)std::min<int64_t>(h->B, (int64_t)h->sm_count * 8);
+  const long long stride = h->dim + h->dof * h->dof;
+  if (h->dim == 4) ensemble_stats_kernel<4><<<grid, 256, 0, h->stream>>>(h->d_state, stride, h->B, dout);
+  else ensemble_stats_kernel<7><<<grid, 256, 0, h->stream>>>(h->d_state, stride, h->B, dout);
+  return UWVKF_OK;
+}
+}  // namespace uwvkf
 
+// ======================================================================================================
 namespace {
 
 constexpr int kFastWarps = 12, kSlowWarps = 6;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
+}  // namespace
+namespace uwvkf {
 int ensure_tmp(uwvkf_handle h, size_t bytes) {
   if (h->tmp_bytes >= bytes) return UWVKF_OK;
   if (h->d_tmp) cudaFree(h->d_tmp);
@@ -234,6 +215,8 @@ int ensure_tmp(uwvkf_handle h, size_t bytes) {
   h->tmp_bytes = bytes;
   return UWVKF_OK;
 }
+}  // namespace uwvkf
+namespace {
 
 void fill_tmerc(TMercConst &tm, double lat0, double lon0) {
   const double a = 6378137.0, f = 1.0 / 298.257223563;
@@ -309,6 +292,8 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   return slow ? launch_pose<53, kSlowWarps>(h, L) : launch_pose<19, kFastWarps>(h, L);
 }
 
+}  // namespace
+namespace uwvkf {
 // stage a host/device input array on the device; returns the device pointer to use
 int stage(uwvkf_handle h, const void *src, size_t bytes, size_t cap, int memspace, void **slot, const void **out) {
   if (!src) { *out = nullptr; return UWVKF_OK; }
@@ -318,6 +303,8 @@ int stage(uwvkf_handle h, const void *src, size_t bytes, size_t cap, int memspac
   *out = *slot;
   return UWVKF_OK;
 }
+}  // namespace uwvkf
+namespace {
 
 int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, int R_per_filter, const double *aux,
                    const uint8_t *valid, int memspace, pose::Op &op) {
@@ -358,21 +345,16 @@ int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, i
   return UWVKF_OK;
 }
 
-#define REQUIRE(h, k)                                                                  \
-  if (!(h)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");                    \
-  if ((h)->kind != (k)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "wrong filter kind for this call"); \
-  CK(cudaSetDevice((h)->device));
-
 }  // namespace
 
 extern "C" {
 
-const char *uwvkf_last_error(void) { return g_err.c_str(); }
+const char *uwvkf_last_error(void) { return uwvkf::g_err.c_str(); }
 const char *uwvkf_version(void) { return "uwvkf 0.1 (sm_100a)"; }
 
 int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) {
   if (!out || batch <= 0) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
-  if (filter_kind != UWVKF_FILTER_POSE) return fail(UWVKF_ERR_UNSUPPORTED, "filter kind not built yet");
+  if (filter_kind < UWVKF_FILTER_POSE || filter_kind > UWVKF_FILTER_INDIRECT_POSE) return fail(UWVKF_ERR_INVALID_ARGUMENT, "unknown filter kind");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -384,6 +366,12 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
   uwvkf_handle h = new uwvkf_filter_s();
   h->kind = filter_kind; h->B = batch; h->device = device;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (filter_kind != UWVKF_FILTER_POSE) {
+    int rc = small_create(h);
+    if (rc) { uwvkf_destroy(h); return rc; }
+    *out = h;
+    return UWVKF_OK;
+  }
   std::vector<uint16_t> lut(pose::NP);
   for (int j = 0; j < pose::N; ++j) for (int i = j; i < pose::N; ++i) lut[pose::cidx(i, j)] = (uint16_t)(i | (j << 8));
   cudaError_t ce = cudaMemcpyToSymbol(g_lut, lut.data(), lut.size() * sizeof(uint16_t));
@@ -402,8 +390,8 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
     uwvkf_destroy(h);
     return fail(UWVKF_ERR_CUDA, "allocation failed: " + msg);
   }
-  h->pp.mean_tol = 1e-9;
-  h->pp.mean_max_it = 100;
+  h->pp.mean_tol = h->mean_tol;
+  h->pp.mean_max_it = h->mean_max_it;
   *out = h;
   return UWVKF_OK;
 }
@@ -412,7 +400,8 @@ int uwvkf_destroy(uwvkf_handle h) {
   if (!h) return UWVKF_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
-  cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_w); cudaFree(h->d_valid); cudaFree(h->d_tmp);
+  cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp);
+  small_destroy(h);
   delete h;
   return UWVKF_OK;
 }
@@ -433,14 +422,17 @@ int64_t uwvkf_kernel_launches(uwvkf_handle h) { return h ? h->launches : 0; }
 
 int uwvkf_set_mean_policy(uwvkf_handle h, double tol, int max_it) {
   if (!h || max_it < 1 || !(tol >= 0)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad policy");
-  h->pp.mean_tol = tol; h->pp.mean_max_it = max_it;
+  h->pp.mean_tol = h->mean_tol = tol;
+  h->pp.mean_max_it = h->mean_max_it = max_it;
   return UWVKF_OK;
 }
 
 int uwvkf_set_state(uwvkf_handle h, const double *mu, const double *cov, int64_t cov_stride, int64_t first, int64_t count,
                     int memspace) {
-  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
   if (!mu || !cov || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad range or null pointer");
+  if (h->kind != UWVKF_FILTER_POSE) return small_set_state(h, mu, cov, cov_stride, first, count, memspace);
   if (cov_stride != 0 && cov_stride != pose::N * pose::N) return fail(UWVKF_ERR_INVALID_ARGUMENT, "cov_stride must be 0 (shared) or DOF*DOF");
   const size_t cb = (size_t)pose::N * pose::N * sizeof(double), mb = (size_t)pose::DIM * sizeof(double);
   if (memspace == UWVKF_DEVICE) {
@@ -468,8 +460,10 @@ int uwvkf_set_state(uwvkf_handle h, const double *mu, const double *cov, int64_t
 }
 
 int uwvkf_get_state(uwvkf_handle h, double *mu, double *cov, int64_t first, int64_t count, int memspace) {
-  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
   if ((!mu && !cov) || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad range or null pointer");
+  if (h->kind != UWVKF_FILTER_POSE) return small_get_state(h, mu, cov, first, count, memspace);
   const size_t cb = (size_t)pose::N * pose::N * sizeof(double), mb = (size_t)pose::DIM * sizeof(double);
   if (memspace == UWVKF_DEVICE) {
     pose_unpack_kernel<<<1024, 256, 0, h->stream>>>(h->d_state, mu, cov, first, count);
@@ -494,8 +488,13 @@ int uwvkf_get_state(uwvkf_handle h, double *mu, double *cov, int64_t first, int6
 }
 
 int uwvkf_set_process_noise(uwvkf_handle h, const double *Q) {
-  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
   if (!Q) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null Q");
+  if (h->kind != UWVKF_FILTER_POSE) {
+    for (int k = 0; k < h->dof * h->dof; ++k) h->Qh[k] = Q[k];
+    return UWVKF_OK;
+  }
   std::vector<double> packed(pose::NP);
   for (int j = 0; j < pose::N; ++j) for (int i = j; i < pose::N; ++i) packed[pose::cidx(i, j)] = Q[i * pose::N + j];
   CK(cudaMemcpyAsync(h->d_Q, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -572,8 +571,10 @@ int uwvkf_pose_get_rotation_rate(uwvkf_handle h, double *out) {
 }
 
 int uwvkf_predict(uwvkf_handle h, double dt) {
-  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
   if (std::isnan(dt)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "dt is NaN");
+  if (h->kind != UWVKF_FILTER_POSE) return small_predict(h, dt);
   pose::Op op{};
   op.type = 0; op.dt = dt;
   return run_pose(h, 1, &op);
@@ -638,11 +639,13 @@ int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose7) {
 
 int64_t uwvkf_ensemble_stats_size(uwvkf_handle h) {
   if (!h) return 0;
-  return 1 + pose::DIM + pose::DIM * (pose::DIM + 1) / 2;
+  const int d = h->kind == UWVKF_FILTER_POSE ? pose::DIM : h->dim;
+  return 1 + d + d * (d + 1) / 2;
 }
 
 int uwvkf_ensemble_stats(uwvkf_handle h, double *out, int memspace) {
-  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
   if (!out) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null output");
   const size_t bytes = (size_t)uwvkf_ensemble_stats_size(h) * sizeof(double);
   double *dout = out;
@@ -652,8 +655,13 @@ int uwvkf_ensemble_stats(uwvkf_handle h, double *out, int memspace) {
     dout = h->d_tmp;
   }
   CK(cudaMemsetAsync(dout, 0, bytes, h->stream));
-  int grid = (int)std::min<int64_t>(h->B, (int64_t)h->sm_count * 8);
-  ensemble_stats_kernel<pose::DIM><<<grid, 256, 0, h->stream>>>(h->d_state, pose::BLK, h->B, dout);
+  if (h->kind != UWVKF_FILTER_POSE) {
+    int rc = small_ensemble_stats(h, dout);
+    if (rc) return rc;
+  } else {
+    int grid = (int)std::min<int64_t>(h->B, (int64_t)h->sm_count * 8);
+    ensemble_stats_kernel<pose::DIM><<<grid, 256, 0, h->stream>>>(h->d_state, pose::BLK, h->B, dout);
+  }
   CK(cudaGetLastError());
   h->launches++;
   if (memspace == UWVKF_HOST) {

@@ -228,3 +228,101 @@ def pose_initial_batch(filters, cfg=None, spread=1.0, with_cov=True):
     mu[:, 6] = np.cos(half)
     cov = np.tile(cov0, (B, 1, 1)) if with_cov else cov0
     return mu, cov
+
+
+# ---- VelocityUKF / BottomUKF / IndirectPoseUKF scenarios (BASELINE.json configs 1, 2, 5) ---------------------
+def uwv_params_flat():
+    """flat uwv_dynamic_model::UWVParameters (116) of SYNTH-1: SIMPLE damping, W = B = 1500 N, r_g = r_b = 0."""
+    M, Dl, Dq = uwv_matrices()
+    p = np.zeros(116)
+    p[0:36], p[36:72], p[72:108] = M.ravel(), Dl.ravel(), Dq.ravel()
+    p[114] = p[115] = 1500.0
+    return p
+
+
+def velocity_inputs(filters, step, dt=0.01):
+    """thrust / gyro / DVL / pressure samples for VelocityUKF (Appendix F)."""
+    filters = np.asarray(filters, dtype=np.uint64)
+    B = filters.shape[0]
+    t = step * dt
+    tau = np.array([10 + 20 * np.sin(0.31 * t), 5 * np.sin(0.63 * t), 2 * np.sin(0.2 * t), 0.0, 0.0, 1.0 * np.sin(0.1 * t)])
+    efforts = np.tile(tau, (B, 1)) + 0.1 * np.stack([noise(filters, step, 60 + k) for k in range(6)], -1)
+    gyro = np.tile(np.array([0.0, 0.0, 0.05 * np.sin(0.02 * t)]), (B, 1)) + 1e-4 * np.stack([noise(filters, step, 70 + k) for k in range(3)], -1)
+    tr = truth(t)
+    dvl = tr["vb"] + 0.01 * np.stack([noise(filters, step, 80 + k) for k in range(3)], -1)
+    pressure = (tr["z"] + 0.05 * noise(filters, step, 90)).reshape(B, 1)
+    return dict(efforts=np.ascontiguousarray(efforts), gyro=np.ascontiguousarray(gyro), dvl=np.ascontiguousarray(dvl),
+                pressure=np.ascontiguousarray(pressure))
+
+
+def velocity_initial_batch(filters):
+    filters = np.asarray(filters, dtype=np.uint64)
+    B = filters.shape[0]
+    mu = np.zeros((B, 4))
+    mu[:, 0] = 1.0
+    mu[:, 0:3] += 0.1 * np.stack([noise(filters, 0xFFFFFE, k) for k in range(3)], -1)
+    mu[:, 3] = -10.0 + 0.2 * noise(filters, 0xFFFFFE, 3)
+    cov = np.tile(np.diag([0.1, 0.1, 0.1, 1.0]), (B, 1, 1))
+    return mu, cov
+
+
+# DVL beam geometry (Janus, 30 deg) and a sloped sea floor for BottomUKF
+BEAMS = np.array([[np.sin(np.pi / 6) * np.cos(a), np.sin(np.pi / 6) * np.sin(a), -np.cos(np.pi / 6)] for a in
+                  (np.pi / 4, 3 * np.pi / 4, 5 * np.pi / 4, 7 * np.pi / 4)])
+BEAM_ORIGIN = np.array([0.1, 0.0, -0.2])
+
+
+def bottom_initial_batch(filters):
+    filters = np.asarray(filters, dtype=np.uint64)
+    B = filters.shape[0]
+    mu = np.zeros((B, 4))
+    mu[:, 0] = 5.0 + 0.5 * noise(filters, 0xFFFFFD, 0)
+    n = np.stack([0.05 * noise(filters, 0xFFFFFD, 1), 0.05 * noise(filters, 0xFFFFFD, 2), np.ones(B)], -1)
+    mu[:, 1:4] = n / np.linalg.norm(n, axis=1, keepdims=True)
+    cov = np.tile(np.diag([1.0, 0.05, 0.05]), (B, 1, 1))
+    return mu, cov
+
+
+def bottom_inputs(filters, step, dt=0.1):
+    filters = np.asarray(filters, dtype=np.uint64)
+    B = filters.shape[0]
+    t = step * dt
+    vel = np.tile(np.array([1.0, 0.2 * np.sin(0.1 * t), -0.05]), (B, 1))
+    n_true = np.array([0.08, -0.03, 1.0])
+    n_true /= np.linalg.norm(n_true)
+    d_true = 5.5 + 0.05 * t
+    ranges = np.stack([((np.array([0, 0, -d_true]) - BEAM_ORIGIN) @ n_true) / (BEAMS[k] @ n_true) + 0.02 * noise(filters, step, 110 + k)
+                       for k in range(4)], -1)
+    nm = n_true + 0.01 * np.stack([noise(filters, step, 120 + k) for k in range(3)], -1)
+    nm /= np.linalg.norm(nm, axis=1, keepdims=True)
+    return dict(velocity=np.ascontiguousarray(vel), ranges=np.ascontiguousarray(ranges), normal=np.ascontiguousarray(nm))
+
+
+CAMERA = np.array([800.0, 800.0, 320.0, 240.0])
+CAM_IN_BODY = np.array([0.3, 0.0, -0.1, 0.5, -0.5, 0.5, -0.5])      # camera z axis along body x
+MARKER_POSE = np.array([4.0, 0.3, -0.2, 0.0, 0.0, 0.0, 1.0])
+MARKER_FEATURES = 0.1 * np.array([[0.0, -1.0, -1.0], [0.0, 1.0, -1.0], [0.0, 1.0, 1.0], [0.0, -1.0, 1.0]])
+
+
+def indirect_inputs(filters, step, dt=0.01):
+    """pose reference (dead-reckoned body pose with a slowly growing offset) and marker corner pixels."""
+    filters = np.asarray(filters, dtype=np.uint64)
+    B = filters.shape[0]
+    t = step * dt
+    yaw = 0.05 * np.sin(0.3 * t)
+    ref = np.tile(np.array([0.2 * t, 0.05 * np.sin(t), 0.0, 0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2)]), (B, 1))
+    # true body pose = reference shifted by a constant error (what the filter should estimate)
+    err_t = np.array([0.15, -0.1, 0.05])
+    c, s = np.cos(yaw), np.sin(yaw)
+    Rb = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    body_t = ref[0, 0:3] + Rb @ err_t
+    Rc = np.array([[0, 0, 1.0], [-1.0, 0, 0], [0, -1.0, 0]])         # rotation of CAM_IN_BODY quaternion
+    cam_t = body_t + Rb @ CAM_IN_BODY[0:3]
+    Rcn = Rb @ Rc
+    px = np.zeros((B, 4, 2))
+    for k in range(4):
+        pw = MARKER_POSE[0:3] + MARKER_FEATURES[k]
+        pc = Rcn.T @ (pw - cam_t)
+        uv = np.array([CAMERA[0] * pc[0] / pc[2] + CAMERA[2], CAMERA[1] * pc[1] / pc[2] + CAMERA[3]])
+        px[:, k, :] = uv + 0.5 * np.stack([noise(filters, step, 130 + 2 * k), noise(filters, step, 131 + 2 * k)], -1)
+    return dict(pose_ref=np.ascontiguousarray(ref), px=np.ascontiguousarray(px))

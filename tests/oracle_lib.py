@@ -169,3 +169,64 @@ def quat_rot(q, v):
     out = np.zeros(3)
     lib().orc_quat_rot(_p(_c(q)), _p(_c(v)), _p(out))
     return out
+
+
+# ---- small filters ------------------------------------------------------------------------------------------
+def vel_setup_motion_model(mu, gyro):
+    sim = np.zeros(10)
+    lib().orc_vel_setup_motion_model(_p(_c(mu)), _p(_c(gyro)), _p(sim))
+    return sim
+
+
+def vel_predict(mu, cov, Q, sim, gyro, efforts, uwv, dt, policy=None):
+    mu, cov, sim = _c(mu).copy(), _c(cov).copy(), _c(sim).copy()
+    st = lib().orc_vel_predict(_p(mu), _p(cov), _p(_c(Q)), _p(sim), _p(_c(gyro)), _p(_c(efforts)), _p(_c(uwv)), C.c_double(dt),
+                               _p(_c(policy)))
+    return mu, cov, sim, st
+
+
+def vel_update(kind, mu, cov, z, R, policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    st = lib().orc_vel_update(C.c_int(kind), _p(mu), _p(cov), _p(_c(z)), _p(_c(R)), _p(_c(policy)))
+    return mu, cov, st
+
+
+def bottom_predict(mu, cov, Q, velocity, dt, policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    st = lib().orc_bottom_predict(_p(mu), _p(cov), _p(_c(Q)), _p(_c(velocity)), C.c_double(dt), _p(_c(policy)))
+    return mu, cov, st
+
+
+def bottom_update_range(mu, cov, z, R, unit_direction, origin, policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    st = lib().orc_bottom_update_range(_p(mu), _p(cov), _p(_c(z)), _p(_c(R)), _p(_c(unit_direction)), _p(_c(origin)),
+                                       _p(_c(policy)))
+    return mu, cov, st
+
+
+def bottom_update_normal(mu, cov, z, R, policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    st = lib().orc_bottom_update_normal(_p(mu), _p(cov), _p(_c(z)), _p(_c(R)), _p(_c(policy)))
+    return mu, cov, st
+
+
+def indirect_predict(mu, cov, Q, tau, dt, policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    st = lib().orc_indirect_predict(_p(mu), _p(cov), _p(_c(Q)), C.c_double(tau), C.c_double(dt), _p(_c(policy)))
+    return mu, cov, st
+
+
+def indirect_update_features(mu, cov, px, pxcov, feature_pos, marker_pose, cov_marker, camera, cam_in_body, pose_ref,
+                             policy=None):
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    px = _c(px)
+    st = lib().orc_indirect_update_features(_p(mu), _p(cov), C.c_int(px.shape[0]), _p(px), _p(_c(pxcov)), _p(_c(feature_pos)),
+                                            _p(_c(marker_pose)), _p(_c(cov_marker)), _p(_c(camera)), _p(_c(cam_in_body)),
+                                            _p(_c(pose_ref)), _p(_c(policy)))
+    return mu, cov, st
+
+
+def indirect_corrected_pose(mu, pose_ref):
+    out = np.zeros(7)
+    lib().orc_indirect_corrected_pose(_p(_c(mu)), _p(_c(pose_ref)), _p(out))
+    return out
