@@ -318,3 +318,22 @@ def test_mean_policy_is_honoured(pkg, syn, scen):
         omu, ocov, st, _ = orc.pose_predict(mu[f], cov[f], scen["Q"], w[f], scen["par"], off[f], DT, policy=pol)
         assert state_err(gmu[f], omu) <= TOL_STATE and cov_err(gcov[f], ocov) <= TOL_COV
     ukf.close()
+
+
+def test_matches_committed_golden_sequence(pkg, syn, scen):
+    """CUDA path vs the committed fixture tests/golden/pose_sequence.npz (free-running, no re-synchronisation)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pose_sequence.npz"))
+    mus, covs = g["mu"], g["cov"]
+    B = mus.shape[1]
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    for s in range(1, int(g["steps"]) + 1):
+        inp = syn.pose_inputs(filt, s)
+        ukf.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        ukf.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+        if s % 4 == 0:
+            ukf.integrate_measurement(pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE)
+            ukf.integrate_measurement(pkg.POSE_WATER_VELOCITY, inp["adcp"], syn.R_ADCP, aux=np.array([0.5]))
+        gmu, gcov = ukf.get_state()
+        assert_parity(gmu, gcov, mus[s], covs[s], f"golden step {s}")
+    ukf.close()

@@ -159,3 +159,24 @@ def test_small_filter_ensemble_stats(pkg, syn):
     out = ukf.ensemble_stats()
     assert out[0] == B and np.allclose(out[1:5], mu.sum(0)) and np.allclose(out[5:], (mu.T @ mu)[np.tril_indices(4)])
     ukf.close()
+
+
+def test_bottom_matches_committed_golden_sequence(pkg, syn):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "small_sequences.npz"))["bottom"]
+    B = 3
+    filt = np.arange(B)
+    mu, cov = syn.bottom_initial_batch(filt)
+    ukf = pkg.BottomUKFBatch(B)
+    ukf.set_state(mu, cov)
+    for s in range(1, 11):
+        inp = syn.bottom_inputs(filt, s)
+        ukf.set_velocity(inp["velocity"])
+        ukf.prediction_step(0.1)
+        for k in range(4):
+            ukf.integrate_range(inp["ranges"][:, k].copy(), np.array([4e-4]), syn.BEAMS[k], syn.BEAM_ORIGIN)
+        if s % 5 == 0:
+            ukf.integrate_normal(inp["normal"], 1e-4 * np.eye(2))
+        gmu, gcov = ukf.get_state()
+        check(gmu, gcov, g[s][:, :4], g[s][:, 4:].reshape(B, 3, 3), f"bottom golden step {s}")
+    ukf.close()
