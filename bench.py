@@ -89,9 +89,18 @@ def scenario():
     return syn, cfg, syn.pose_params(cfg), syn.pose_process_noise(cfg, DT)
 
 
+def host_cores():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(syn, cfg, par, Q, nfilt, nsteps, nthreads=0):
     """Times the CPU oracle (literal ukfom recipe = the reference's algorithm) on nfilt filters x nsteps fused steps."""
     import oracle_lib as orc
+    nthreads = nthreads or host_cores()
     filt = np.arange(nfilt)
     mu, cov = syn.pose_initial_batch(filt, cfg)
     mu, cov = np.ascontiguousarray(mu), np.ascontiguousarray(cov)
@@ -108,8 +117,8 @@ def run_reference(args):
         return
     import oracle_lib as orc
     syn, cfg, par, Q = scenario()
-    cores = orc.num_threads()
-    nf = args.ref_filters or 4 * cores
+    cores = host_cores()
+    nf = args.ref_filters or 128 * cores
     cpu_reference_run(syn, cfg, par, Q, cores, 1)  # touch
     for _ in range(args.warmup):
         cpu_reference_run(syn, cfg, par, Q, nf, 1)
@@ -261,13 +270,15 @@ def main():
                 "gpu_launches": launches, "gpu_launches_e2e": e2e_launches, "clocks": clocks, "filter_faults": faults,
                 "ensemble": {"filters_reduced": n_total, "allreduce_ms": ens_ms}}
         if world == 1 and not args.no_cpu_baseline:
-            import oracle_lib as orc
-            cores = orc.num_threads()
-            t_probe = cpu_reference_run(syn, cfg, par, Q, cores, 1)
-            nsteps = max(1, min(200, int(12.0 / max(t_probe, 1e-3) / 4)))
-            secs = cpu_reference_run(syn, cfg, par, Q, 4 * cores, nsteps)
-            line["cpu_baseline"] = {"value": 4 * cores * nsteps / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{4 * cores} filters x {nsteps} fused steps (oracle, OpenMP over filters, {secs:.1f} s)"}
+            cores = host_cores()
+            nf = 64 * cores
+            cpu_reference_run(syn, cfg, par, Q, nf, 1)                      # warm-up (thread team, page faults)
+            t_probe = cpu_reference_run(syn, cfg, par, Q, nf, 2) / 2        # seconds per pass over nf filters
+            nsteps = max(2, min(2000, int(12.0 / max(t_probe, 1e-4))))       # ~12 s of wall time on all cores
+            secs = cpu_reference_run(syn, cfg, par, Q, nf, nsteps)
+            line["cpu_baseline"] = {"value": nf * nsteps / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{nf} filters x {nsteps} fused steps (oracle = literal ukfom recipe, OpenMP over "
+                                              f"filters on {cores} threads, {secs:.1f} s)"}
         print(json.dumps(line), flush=True)
     ukf.close()
     if world > 1:
