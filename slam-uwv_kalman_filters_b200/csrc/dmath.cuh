@@ -82,10 +82,28 @@ __device__ __forceinline__ Quat so3_exp(const Vec3 &v, double scale) {
   double m = s * h;
   return Quat{m * v.x, m * v.y, m * v.z, c};
 }
+// MTK SO3::log: s = 2 atan(|u| / w) / |u|.  For |u|^2 <= 2.5e-3 w^2 (rotation below ~0.1 rad, every sigma-point
+// deviation of a converged filter) atan(x)/x is evaluated by its alternating series in t = x^2 -- truncation
+// t^7/15 < 5e-20, i.e. the same double as sqrt + atan + two divisions to 1 ulp -- without sqrt, atan or |u|.
 __device__ __forceinline__ Vec3 so3_log(const Quat &q) {
-  double nv = sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
-  if (nv < kMtkTol) nv = kMtkTol;
-  double s = 2.0 / nv * atan(nv / q.w);
+  double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
+  double w2 = q.w * q.w;
+  double s;
+  if (n2 <= 2.5e-3 * w2) {
+    double iw = 1.0 / q.w;
+    double t = n2 * iw * iw;
+    double p = fma(t, 1.0 / 13.0, -1.0 / 11.0);
+    p = fma(p, t, 1.0 / 9.0);
+    p = fma(p, t, -1.0 / 7.0);
+    p = fma(p, t, 1.0 / 5.0);
+    p = fma(p, t, -1.0 / 3.0);
+    p = fma(p, t, 1.0);
+    s = 2.0 * iw * p;
+  } else {
+    double nv = sqrt(n2);
+    if (nv < kMtkTol) nv = kMtkTol;
+    s = 2.0 / nv * atan(nv / q.w);
+  }
   return Vec3{s * q.x, s * q.y, s * q.z};
 }
 __device__ __forceinline__ Quat so3_boxplus(const Quat &q, const Vec3 &v, double scale) { return qmul(q, so3_exp(v, scale)); }

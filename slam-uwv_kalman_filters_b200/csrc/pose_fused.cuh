@@ -1,0 +1,538 @@
+// PoseUKF fused step kernel, version 2 ("panel + stream").
+//
+// Same mathematics as pose_engine.cuh (prefix-structured unscented transform) with a
+// different residency plan: every op of the fast path (predict k=15, DVL k=9, XY/Z k<=3, acceleration k=19,
+// apply_delta k=6) reads and writes only the first KP columns of Sigma -- the PANEL, a prefix of the
+// column-packed block.  The trailing (53-KP)^2/2 entries are touched by exactly one elementwise expression,
+//     Sigma_new[a][b] = f_a f_b Sigma_old[a][b] + dt^2 Q[a][b] - sum_c (K S)[a][c] K[b][c],
+// so they never enter shared memory: after the panel work is done each warp streams them HBM -> registers ->
+// HBM once, column by column, with the per-row factors (f_a, (KS)_a) held in registers by the lane that owns
+// row a and the per-column factors (f_b, K_b) read as one shared-memory broadcast.  Shared memory per warp drops
+// from 17.6 KB to ~10.8 KB (more resident warps) and the two 1431-entry passes of v1 (LUT decode + 8 scattered
+// shared loads per entry) disappear.
+#pragma once
+#include "pose_engine.cuh"
+
+namespace uwvkf {
+namespace pose {
+
+constexpr int M_NONE = -1;
+
+template <int HAS_PREDICT, int KIND>
+struct FusedCfg {
+  static constexpr int KM = (KIND == M_NONE) ? 0 : Meas<KIND == M_NONE ? M_XY : KIND>::K;   // KIND in {NONE, XY, Z, VELOCITY, ACCELERATION}
+  static constexpr int KA = (KIND == M_NONE) ? 0 : 6;                       // apply_delta prefix
+  static constexpr int K0 = HAS_PREDICT ? 15 : 0;
+  static constexpr int KP = (K0 > KM ? (K0 > KA ? K0 : KA) : (KM > KA ? KM : KA));   // panel width
+  static constexpr int PANEL = KP * N - (KP * (KP - 1)) / 2;                // doubles in the panel
+  static constexpr int PANEL_E = ((PANEL + 1) / 2) * 2;
+  static constexpr int KL = KP;                                             // largest leading factor
+  static constexpr int LSZ = ((KL * (KL + 1) / 2 + 1) / 2) * 2;
+  static constexpr int KE = ((KL + 1) / 2) * 2;
+  // per-warp shared layout (doubles)
+  static constexpr int O_MU = 0;                   // 56
+  static constexpr int O_S = 56;                   // panel (same indexing as the full packed array)
+  static constexpr int O_L = O_S + PANEL_E;
+  static constexpr int O_INVD = O_L + LSZ;
+  static constexpr int O_G = O_INVD + KE;          // 3 x KE
+  static constexpr int O_ROWK = O_G + 3 * KE;      // [53][4] = K0 K1 K2 f   (column-side broadcast data)
+  static constexpr int TOTAL = ((O_ROWK + 53 * 4 + 1) / 2) * 2;
+};
+
+__device__ __forceinline__ int coloff(int j) { return j * N - ((j * (j - 1)) >> 1) - j; }   // cidx(i, j) = coloff(j) + i
+
+// T[c] = sum_{b<K} G[c][b] * Sigma[b][x] for the two rows x0 = lane, x1 = lane + 32 owned by this lane (registers)
+template <int K, int M, int KE>
+__device__ __forceinline__ void g_times_sigma_reg(const double *G, const double *S, int lane, double (&T)[2][M]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = lane + 32 * h;
+    const int cox = coloff(x < N ? x : 0);
+#pragma unroll
+    for (int c = 0; c < M; ++c) T[h][c] = 0.0;
+    if (x < N) {
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        const int e = (x >= b) ? (coloff(b) + x) : (cox + b);
+        const double s = S[e];
+#pragma unroll
+        for (int c = 0; c < M; ++c) T[h][c] = fma(G[c * KE + b], s, T[h][c]);
+      }
+    }
+  }
+}
+
+// Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh); T stays in registers.
+template <int K, int KE>
+__device__ __forceinline__ Quat ori_transform_reg(const double *S, const double *Lw, const double *invd, double *G, const Quat &qp,
+                                                  int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status) {
+  const bool act = p < 2 * K + 1;
+  const bool on = act && p > 0;
+  const int j = (p - 1) >> 1;
+  Quat qa[1] = {qp};
+  double wa[1] = {p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0)};
+  Quat r = so3_mean<1>(qa, wa, P.mean_tol, P.mean_max_it, status);
+  Vec3 a = so3_boxminus(qp, r);
+  const double hw = 0.5 * wa[0];
+  soo[0] = warp_sum(hw * a.x * a.x);
+  soo[1] = warp_sum(hw * a.y * a.x);
+  soo[2] = warp_sum(hw * a.z * a.x);
+  soo[3] = warp_sum(hw * a.y * a.y);
+  soo[4] = warp_sum(hw * a.z * a.y);
+  soo[5] = warp_sum(hw * a.z * a.z);
+  double nx = __shfl_down_sync(kFull, a.x, 1), ny = __shfl_down_sync(kFull, a.y, 1), nz = __shfl_down_sync(kFull, a.z, 1);
+  if (on && (p & 1)) {
+    G[0 * KE + j] = 0.5 * (a.x - nx);
+    G[1 * KE + j] = 0.5 * (a.y - ny);
+    G[2 * KE + j] = 0.5 * (a.z - nz);
+  }
+  __syncwarp();
+  solve_right<K, 3>(G, KE, Lw, invd, lane);
+  g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
+  return r;
+}
+
+// per-lane row data for the rows x0 = lane and x1 = lane + 32
+struct RowData {
+  double f[2];       // diagonal of the affine process map (1 when no predict)
+  double ks[2][3];   // (K S) rows of the accepted update (0 when none)
+  double kk[2][3];   // K rows
+};
+
+// ---------------------------------------------------------------------------------------------------------
+template <int HAS_PREDICT, int KIND, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
+  using C = FusedCfg<HAS_PREDICT, KIND>;
+  constexpr int KP = C::KP, KE = C::KE;
+  extern __shared__ __align__(16) double smem[];
+  double *Qs = smem;                                 // packed Q (only when HAS_PREDICT)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w = smem + (HAS_PREDICT ? 1432 : 0) + warp * C::TOTAL;
+  double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G, *rowK = w + C::O_ROWK;
+  if (HAS_PREDICT) {
+    for (int e = threadIdx.x; e < NP; e += blockDim.x) Qs[e] = a.Q[e];
+    __syncthreads();
+  }
+  const Op &op0 = a.ops[0];
+  const Op &opu = a.ops[HAS_PREDICT ? 1 : 0];
+  const double dt = HAS_PREDICT ? op0.dt : 0.0;
+  const double dt2 = dt * dt;
+  const int x0 = lane, x1 = lane + 32;
+
+  for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
+    double *blk = a.state + f * BLK;
+    // ---- stage mu + panel (a prefix of the block: [mu 54 | pad 2 | panel ...]) -------------------------------
+    {
+      const double2 *src = reinterpret_cast<const double2 *>(blk);
+      double2 *dst = reinterpret_cast<double2 *>(w);
+      constexpr int NV = (56 + C::PANEL_E) / 2;
+#pragma unroll 4
+      for (int k = lane; k < NV; k += 32) dst[k] = __ldcs(src + k);
+    }
+    __syncwarp();
+    unsigned st = 0;
+    bool predicted = false, updated = false;
+    RowData rd;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rd.f[h] = 1.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { rd.ks[h][c] = 0.0; rd.kk[h][c] = 0.0; }
+    }
+    double add = 0.0;
+
+    // =================================== predict (k = 15) ====================================================
+    if constexpr (HAS_PREDICT) {
+      constexpr int K = 15;
+      const double *off = a.offsets + f * NOFF;
+      const double *wm_g = a.rot_rate + f * 3;
+      if (chol_leading<K>(S, Lw, invd, lane)) {
+        const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
+        const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};
+        const int p = lane;
+        const bool on = p > 0 && p < 2 * K + 1;
+        const int j = (p - 1) >> 1;
+        const double sg = (p & 1) ? 1.0 : -1.0;
+        auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+        Quat qp;
+        {
+          double px = mu[P_POS] + d(0), py = mu[P_POS + 1] + d(1);
+          Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
+          Vec3 wb{wm_g[0] - (mu[P_BG] + d(12)), wm_g[1] - (mu[P_BG + 1] + d(13)), wm_g[2] - (mu[P_BG + 2] + d(14))};
+          double lat = tmerc_nav_to_lat(P.tm, px, py);
+          double sl, cl;
+          sincos(lat, &sl, &cl);
+          Vec3 wn = qrot(qq, wb);
+          wn.x -= kEarthW * cl;
+          wn.z -= kEarthW * sl;
+          qp = so3_boxplus(qq, wn, dt);
+        }
+        double soo[6], T[2][3];
+        Quat r = ori_transform_reg<K, KE>(S, Lw, invd, G, qp, p, P, soo, T, lane, st);
+        // effective process noise pieces (reference src/PoseUKF.cpp:448-460)
+        double qoo[6];
+        {
+          double Rm[9], Qo[9], t[9];
+          qmat(q, Rm);
+          Qo[0] = Qs[cidx(3, 3)]; Qo[1] = Qs[cidx(4, 3)]; Qo[2] = Qs[cidx(5, 3)];
+          Qo[3] = Qo[1];          Qo[4] = Qs[cidx(4, 4)]; Qo[5] = Qs[cidx(5, 4)];
+          Qo[6] = Qo[2];          Qo[7] = Qo[5];          Qo[8] = Qs[cidx(5, 5)];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) t[i * 3 + b] = Rm[i * 3] * Qo[b] + Rm[i * 3 + 1] * Qo[3 + b] + Rm[i * 3 + 2] * Qo[6 + b];
+          auto rq = [&](int i, int b) { return t[i * 3] * Rm[b * 3] + t[i * 3 + 1] * Rm[b * 3 + 1] + t[i * 3 + 2] * Rm[b * 3 + 2]; };
+          qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
+        }
+        add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
+        rd.f[0] = affine_factor(x0, P, dt);
+        rd.f[1] = x1 < N ? affine_factor(x1, P, dt) : 1.0;
+        double nm0 = 0, nm1 = 0;
+        if (x0 < P_ORI || x0 >= P_VEL) nm0 = affine_mean(x0, mu, off, P, dt);
+        if (x1 < DIM) nm1 = affine_mean(x1, mu, off, P, dt);
+        __syncwarp();
+        // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
+        couple3(S, T_POS, T_VEL, dt, lane);
+        couple3(S, T_VEL, T_ACC, dt, lane);
+#pragma unroll
+        for (int b = 0; b < KP; ++b) {
+          if (b >= 3 && b < 6) continue;
+          const double fb = affine_factor(b, P, dt);
+          const int cb = coloff(b);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int x = lane + 32 * h;
+            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = rd.f[h] * fb * S[cb + x] + dt2 * Qs[cb + x];
+          }
+        }
+        // orientation rows/cols: T F^T (+ Q cross terms)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int x = lane + 32 * h;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            // coupled partner: T[c][x+6] for x in pos, T[c][x+3] for x in vel (both in round 0)
+            double t6 = __shfl_sync(kFull, T[0][c], (lane + 6) & 31), t3 = __shfl_sync(kFull, T[0][c], (lane + 3) & 31);
+            if (x < N && !(x >= 3 && x < 6)) {
+              double tp = rd.f[h] * T[h][c];
+              if (h == 0 && x < 3) tp += dt * t6;
+              else if (h == 0 && x >= T_VEL && x < T_ACC) tp += dt * t3;
+              const int e = x < 3 ? (coloff(x) + 3 + c) : (coloff(3 + c) + x);
+              S[e] = tp + dt2 * Qs[e];
+            }
+          }
+        }
+        if (lane < 6) {
+          int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+          int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+          S[cidx(3 + bi, 3 + bj)] = soo[lane] + dt2 * qoo[lane];
+        }
+        if (x0 < P_ORI || x0 >= P_VEL) mu[x0] = nm0;
+        if (x1 < DIM) mu[x1] = nm1;
+        if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
+        predicted = true;
+        __syncwarp();
+      } else {
+        st |= ST_NOT_SPD;
+      }
+    }
+
+    // =================================== update (k = Meas::K) + apply_delta (k = 6) ==========================
+    if constexpr (KIND != M_NONE) {
+      using MM = Meas<KIND>;
+      constexpr int K = MM::K, M = MM::M;
+      constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
+      bool go = !(opu.valid && !opu.valid[f]);
+      double z[M], Rm[M * M];
+      if (go) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < M; ++k) { z[k] = opu.z[f * M + k]; bad |= isnan(z[k]); }
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) { Rm[k] = opu.Rdev ? opu.Rdev[f * M * M + k] : opu.R[k]; bad |= isnan(Rm[k]); }
+        if (bad) { st |= ST_NAN_MEAS; go = false; }
+      }
+      if (go) {
+        if constexpr (KIND == M_XY) {
+          if (opu.kind == M_GEOGRAPHIC) {   // reference src/PoseUKF.cpp:572-578
+            double px, py;
+            tmerc_world_to_nav(P.tm, z[0], z[1], px, py);
+            Vec3 lever = qrot(Quat{mu[3], mu[4], mu[5], mu[6]}, Vec3{opu.aux[0], opu.aux[1], opu.aux[2]});
+            z[0] = px - lever.x; z[1] = py - lever.y;
+          } else if (opu.kind == M_DELAYED_XY) {   // reference src/PoseUKF.cpp:516-521
+            z[0] = z[0] + (mu[0] - opu.aux[0]); z[1] = z[1] + (mu[1] - opu.aux[1]);
+          }
+        }
+        if (!chol_leading<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
+      }
+      if (go) {
+        double Z[ROUNDS][M], wt[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+          const int p = lane + 32 * r;
+          const bool act = p < NPTS;
+          const bool on = act && p > 0;
+          const int j = (p - 1) >> 1;
+          const double sg = (p & 1) ? 1.0 : -1.0;
+          auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+          MM::eval(mu, d, opu.aux, P, Z[r]);
+          wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
+        }
+        double zb[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) zb[k] = bcast(Z[0][k], 0);
+        {
+          int it = 0;
+          double nrm;
+          do {
+            nrm = 0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+              double m = 0;
+#pragma unroll
+              for (int r = 0; r < ROUNDS; ++r) m = fma(wt[r], Z[r][k] - zb[k], m);
+              m = warp_sum(m) / double(2 * N + 1);
+              zb[k] += m;
+              nrm += m * m;
+            }
+            nrm = sqrt(nrm);
+          } while (nrm > P.mean_tol && ++it < P.mean_max_it);
+          if (it >= P.mean_max_it) st |= ST_MEAN_NOT_CONVERGED;
+        }
+        double Szz[M * M];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int b = 0; b <= i; ++b) {
+            double s = 0;
+#pragma unroll
+            for (int r = 0; r < ROUNDS; ++r) s = fma(0.5 * wt[r] * (Z[r][i] - zb[i]), Z[r][b] - zb[b], s);
+            s = warp_sum(s);
+            Szz[i * M + b] = s + Rm[i * M + b];
+            Szz[b * M + i] = s + Rm[b * M + i];
+          }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+          const int p = lane + 32 * r;
+#pragma unroll
+          for (int k = 0; k < M; ++k) {
+            double src = Z[r][k];
+            if (r + 1 < ROUNDS) { if (lane == 0) src = Z[r + 1 < ROUNDS ? r + 1 : r][k]; }
+            double nxt = __shfl_sync(kFull, src, (lane + 1) & 31);
+            if ((p & 1) && p < NPTS) G[k * KE + ((p - 1) >> 1)] = 0.5 * (Z[r][k] - nxt);
+          }
+        }
+        __syncwarp();
+        solve_right<K, M>(G, KE, Lw, invd, lane);
+        double T[2][M];
+        g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
+        double Si[M * M], nu[M];
+        sym_inverse<M>(Szz, Si);
+#pragma unroll
+        for (int k = 0; k < M; ++k) nu[k] = z[k] - zb[k];
+        double d2 = 0;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int b = 0; b < M; ++b) d2 += nu[i] * Si[i * M + b] * nu[b];
+        const bool gate95 = (KIND == M_XY) && opu.kind == M_GEOGRAPHIC;   // d2p95, reference src/PoseUKF.cpp:578
+        if (gate95 && d2 > 5.991) {
+          st |= ST_GATE_REJECTED;
+        } else {
+          // gain rows, (K S) rows and delta for the rows this lane owns
+          double dl[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double dx = 0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+              double s = 0;
+#pragma unroll
+              for (int c = 0; c < M; ++c) s += T[h][c] * Si[c * M + i];
+              rd.kk[h][i] = s;
+              dx += s * nu[i];
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+              double s = 0;
+#pragma unroll
+              for (int c = 0; c < M; ++c) s += rd.kk[h][c] * Szz[c * M + i];
+              rd.ks[h][i] = s;
+            }
+            dl[h] = dx;
+          }
+          // column-side broadcast copy of K
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int x = lane + 32 * h;
+            if (x < N) { rowK[x * 4 + 0] = rd.kk[h][0]; rowK[x * 4 + 1] = rd.kk[h][1]; rowK[x * 4 + 2] = rd.kk[h][2]; }
+          }
+          __syncwarp();
+          // panel downdate: Sigma[x][b] -= (KS)_x . K_b
+#pragma unroll
+          for (int b = 0; b < KP; ++b) {
+            const int cb = coloff(b);
+            const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int x = lane + 32 * h;
+              if (x >= b && x < N) {
+                double s = S[cb + x];
+                s = fma(-rd.ks[h][0], k0, s);
+                if (M > 1) s = fma(-rd.ks[h][1], k1, s);
+                if (M > 2) s = fma(-rd.ks[h][2], k2, s);
+                S[cb + x] = s;
+              }
+            }
+          }
+          __syncwarp();
+          // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
+          constexpr int KA = 6;
+          if (chol_leading<KA>(S, Lw, invd, lane)) {
+            const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
+            const double d3 = bcast(dl[0], 3), d4 = bcast(dl[0], 4), d5 = bcast(dl[0], 5);
+            const int p = lane;
+            const bool on = p > 0 && p < 2 * KA + 1;
+            const int j = (p - 1) >> 1;
+            const double sg = (p & 1) ? 1.0 : -1.0;
+            auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<KA>(t, j)] : 0.0; };
+            Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
+            double soo[6], TA[2][3];
+            Quat r = ori_transform_reg<KA, KE>(S, Lw, invd, G, qp, p, P, soo, TA, lane, st);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int x = lane + 32 * h;
+              if (x < N && !(x >= 3 && x < 6)) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) S[x < 3 ? (coloff(x) + 3 + c) : (coloff(3 + c) + x)] = TA[h][c];
+              }
+            }
+            if (lane < 6) {
+              int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+              int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+              S[cidx(3 + bi, 3 + bj)] = soo[lane];
+            }
+            // mu (+)= delta on the vector components: tangent x -> stored x (x < 3) or x + 1 (x >= 6)
+            if (x0 < 3) mu[x0] += dl[0];
+            else if (x0 >= 6) mu[x0 + 1] += dl[0];
+            if (x1 < N) mu[x1 + 1] += dl[1];
+            if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
+            updated = true;
+            __syncwarp();
+          } else {
+            // the downdated covariance lost definiteness in its leading block: roll the panel back, drop the update
+            st |= ST_NOT_SPD;
+#pragma unroll
+            for (int b = 0; b < KP; ++b) {
+              const int cb = coloff(b);
+              const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int x = lane + 32 * h;
+                if (x >= b && x < N) {
+                  double s = S[cb + x];
+                  s = fma(rd.ks[h][0], k0, s);
+                  if (M > 1) s = fma(rd.ks[h][1], k1, s);
+                  if (M > 2) s = fma(rd.ks[h][2], k2, s);
+                  S[cb + x] = s;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (!updated) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { rd.ks[h][c] = 0.0; rd.kk[h][c] = 0.0; }
+      }
+    }
+
+    // =================================== write back ===========================================================
+    if (predicted || updated) {
+      // column-side broadcast data for the trailing pass: K_b (zero if no update) and f_b
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = lane + 32 * h;
+        if (x < N) {
+          rowK[x * 4 + 0] = rd.kk[h][0]; rowK[x * 4 + 1] = rd.kk[h][1]; rowK[x * 4 + 2] = rd.kk[h][2];
+          rowK[x * 4 + 3] = rd.f[h];
+        }
+      }
+      __syncwarp();
+      {
+        double2 *dst = reinterpret_cast<double2 *>(blk);
+        const double2 *src = reinterpret_cast<const double2 *>(w);
+        constexpr int NV = (56 + C::PANEL_E) / 2;
+        // the last double2 of the staged prefix may straddle the panel end: it was loaded from the block, and the
+        // extra double (first trailing entry) is rewritten by the trailing pass below, which runs after this copy
+#pragma unroll 4
+        for (int k = lane; k < NV; k += 32) __stcs(dst + k, src[k]);
+      }
+      __syncwarp();
+      // trailing triangle: rows a >= b >= KP, streamed column by column; lane owns rows KP+lane (and KP+32+lane)
+      double *gS = blk + OFF_S;
+      const int a0 = KP + lane, a1 = KP + 32 + lane;
+      // move this lane's row data from "row x = lane / lane+32" ownership to "row KP+lane / KP+32+lane"
+      double fa[2], ksa[2][3];
+      {
+        const int xs0 = a0, xs1 = a1;   // source tangent indices
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int xs = h ? xs1 : xs0;
+          const bool ok = xs < N;
+          const int xr = ok ? xs : 0;
+          fa[h] = ok ? rowK[xr * 4 + 3] : 1.0;
+          // (K S) rows are not in shared memory: fetch them from the owning lane by shuffle
+          const int src_lane = xr & 31, src_h = xr >> 5;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            double v0 = __shfl_sync(kFull, rd.ks[0][c], src_lane), v1 = __shfl_sync(kFull, rd.ks[1][c], src_lane);
+            ksa[h][c] = ok ? (src_h ? v1 : v0) : 0.0;
+          }
+        }
+      }
+      const bool has_a1 = a1 < N;
+      const double q2 = predicted ? dt2 : 0.0;   // rd.f == 1 and add == 0 unless the predict was applied
+      constexpr int CB = 4;                      // columns per batch: all loads of a batch are issued before its stores
+      for (int b0 = KP; b0 < N; b0 += CB) {
+        double v[CB][2];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          const int b = b0 + u;
+          const int cb = coloff(b);
+          v[u][0] = (b < N && a0 >= b && a0 < N) ? __ldcs(gS + cb + a0) : 0.0;
+          v[u][1] = (b < N && has_a1 && a1 >= b) ? __ldcs(gS + cb + a1) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          const int b = b0 + u;
+          if (b >= N) break;
+          const int cb = coloff(b);
+          const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2], fb = rowK[b * 4 + 3];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ar = h ? a1 : a0;
+            const bool on = h ? (has_a1 && a1 >= b) : (a0 >= b && a0 < N);
+            if (on) {
+              double s = v[u][h];
+              if (HAS_PREDICT) {
+                s = fa[h] * fb * s + q2 * Qs[cb + ar];
+                if (ar == b && b >= T_WV && b < T_BADCP) s += q2 * add;
+              }
+              s = fma(-ksa[h][0], k0, s); s = fma(-ksa[h][1], k1, s); s = fma(-ksa[h][2], k2, s);
+              __stcs(gS + cb + ar, s);
+            }
+          }
+        }
+      }
+    }
+    if (st && lane == 0) a.status[f] |= st;
+    __syncwarp();
+  }
+}
+
+}  // namespace pose
+}  // namespace uwvkf

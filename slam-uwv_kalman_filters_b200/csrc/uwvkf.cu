@@ -1,5 +1,7 @@
 // uwvkf C ABI (include/uwvkf.h) + kernel launchers.  Thin host code over the CUDA kernels; no CPU path.
 #include "internal.h"
+#include "pose_fused.cuh"
+#include <cstdlib>
 
 namespace uwvkf {
 thread_local std::string g_err;
@@ -202,7 +204,7 @@ int small_ensemble_stats(uwvkf_handle h, double *dout) {
 // ======================================================================================================
 namespace {
 
-constexpr int kFastWarps = 12, kSlowWarps = 6;
+constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = 16;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
 }  // namespace
@@ -278,6 +280,42 @@ int launch_pose(uwvkf_handle h, const pose::Launch &L) {
   return UWVKF_OK;
 }
 
+// v2 fused kernel (pose_fused.cuh): WARPS per CTA is chosen per instantiation from its shared-memory footprint
+template <int HP, int KIND>
+constexpr int fused_warps() {
+  using C = pose::FusedCfg<HP, KIND>;
+  int w = (232448 - (HP ? 1432 * 8 : 0)) / (C::TOTAL * 8);
+  return w > kFusedMaxWarps ? kFusedMaxWarps : w;
+}
+template <int HP, int KIND>
+int launch_fused(uwvkf_handle h, const pose::Launch &L) {
+  using C = pose::FusedCfg<HP, KIND>;
+  constexpr int WARPS = fused_warps<HP, KIND>();
+  size_t smem = (size_t)((HP ? 1432 : 0) + WARPS * C::TOTAL) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  long long need = (L.B + WARPS - 1) / WARPS;
+  int grid = (int)std::min<long long>(need, h->sm_count);
+  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return UWVKF_OK;
+}
+template <int HP>
+int launch_fused_kind(uwvkf_handle h, const pose::Launch &L, int kind) {
+  switch (kind) {
+    case UWVKF_POSE_XY: case UWVKF_POSE_GEOGRAPHIC: case UWVKF_POSE_DELAYED_XY: return launch_fused<HP, pose::M_XY>(h, L);
+    case UWVKF_POSE_Z: return launch_fused<HP, pose::M_Z>(h, L);
+    case UWVKF_POSE_VELOCITY: return launch_fused<HP, pose::M_VELOCITY>(h, L);
+    case UWVKF_POSE_ACCELERATION: return launch_fused<HP, pose::M_ACCELERATION>(h, L);
+  }
+  return fail(UWVKF_ERR_INVALID_ARGUMENT, "measurement kind not handled by the fused kernel");
+}
+bool fast_kind(int kind) { return kind != UWVKF_POSE_PRESSURE && kind != UWVKF_POSE_WATER_VELOCITY; }
+
 int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
   pose::Launch L{};
@@ -288,6 +326,14 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
     L.ops[o] = ops[o];
     if (ops[o].type == 0 && !h->have_Q) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_set_process_noise was not called");
     if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_PRESSURE || ops[o].kind == UWVKF_POSE_WATER_VELOCITY)) slow = true;
+  }
+  // engine selection: "panel + stream" kernel for predict / fast update / predict+fast update, the resident
+  // kernel for pressure and ADCP (prefix 53 / 52 = dense) and, with UWVKF_ENGINE=v1, for everything (cross-checks)
+  static const bool force_v1 = [] { const char *e = std::getenv("UWVKF_ENGINE"); return e && std::string(e) == "v1"; }();
+  if (!force_v1 && !slow) {
+    if (nops == 1 && ops[0].type == 0) return launch_fused<1, pose::M_NONE>(h, L);
+    if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
+    if (nops == 2 && ops[0].type == 0 && ops[1].type == 1) return launch_fused_kind<1>(h, L, ops[1].kind);
   }
   return slow ? launch_pose<53, kSlowWarps>(h, L) : launch_pose<19, kFastWarps>(h, L);
 }
