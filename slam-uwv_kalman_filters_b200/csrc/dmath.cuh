@@ -19,6 +19,30 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(kFull, v, src); }
 
+// 1/sqrt(d) for d > 0: hardware seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps -> full double accuracy (~1 ulp)
+// without the special-case handling of rsqrt(); callers test d > 0 themselves.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double t = d * y;
+  double e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = d * y;
+  e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
+// 1/x (normal range): seed + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
 struct Quat {
   double x, y, z, w;
 };
@@ -59,11 +83,28 @@ __device__ __forceinline__ void qmat(const Quat &q, double R[9]) {
 
 // MTK cos_sinc_sqrt: cos(sqrt(x2)), sin(sqrt(x2))/sqrt(x2)
 __device__ __forceinline__ void cos_sinc_sqrt(double x2, double &c, double &s) {
-  if (x2 >= 1.220703125e-4) {  // eps^(1/4) = 2^-13
+  if (x2 >= 0.0625) {  // |x| >= 0.25: libm, as MTK does above eps^(1/4)
     double x = sqrt(x2), sn, cs;
     sincos(x, &sn, &cs);
     c = cs;
     s = sn / x;
+  } else if (x2 >= 1.220703125e-4) {
+    // between MTK's series bound eps^(1/4) = 2^-13 and 1/16 the reference calls cos/sin of sqrt(x2); the Taylor
+    // polynomials below (truncation < 3e-20) return the same doubles to 1 ulp without sqrt / sincos / division
+    double cc = fma(x2, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+    cc = fma(cc, x2, -1.0 / 3628800.0);
+    cc = fma(cc, x2, 1.0 / 40320.0);
+    cc = fma(cc, x2, -1.0 / 720.0);
+    cc = fma(cc, x2, 1.0 / 24.0);
+    cc = fma(cc, x2, -0.5);
+    c = fma(cc, x2, 1.0);
+    double ss = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    ss = fma(ss, x2, -1.0 / 39916800.0);
+    ss = fma(ss, x2, 1.0 / 362880.0);
+    ss = fma(ss, x2, -1.0 / 5040.0);
+    ss = fma(ss, x2, 1.0 / 120.0);
+    ss = fma(ss, x2, -1.0 / 6.0);
+    s = fma(ss, x2, 1.0);
   } else {
     double cosi = 1., sinc = 1.;
     double term = -0.5 * x2;
@@ -82,17 +123,20 @@ __device__ __forceinline__ Quat so3_exp(const Vec3 &v, double scale) {
   double m = s * h;
   return Quat{m * v.x, m * v.y, m * v.z, c};
 }
-// MTK SO3::log: s = 2 atan(|u| / w) / |u|.  For |u|^2 <= 2.5e-3 w^2 (rotation below ~0.1 rad, every sigma-point
-// deviation of a converged filter) atan(x)/x is evaluated by its alternating series in t = x^2 -- truncation
-// t^7/15 < 5e-20, i.e. the same double as sqrt + atan + two divisions to 1 ulp -- without sqrt, atan or |u|.
+// MTK SO3::log: s = 2 atan(|u| / w) / |u|.  For |u|^2 <= 1e-2 w^2 (rotation below ~0.2 rad, every sigma-point
+// deviation of a working filter) atan(x)/x is evaluated by its alternating series in t = x^2 -- truncation
+// t^10/21 < 5e-22, i.e. the same double as sqrt + atan + two divisions to 1 ulp -- without sqrt, atan or |u|.
 __device__ __forceinline__ Vec3 so3_log(const Quat &q) {
   double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
   double w2 = q.w * q.w;
   double s;
-  if (n2 <= 2.5e-3 * w2) {
-    double iw = 1.0 / q.w;
+  if (n2 <= 1.0e-2 * w2) {
+    double iw = fast_rcp(q.w);
     double t = n2 * iw * iw;
-    double p = fma(t, 1.0 / 13.0, -1.0 / 11.0);
+    double p = fma(t, -1.0 / 19.0, 1.0 / 17.0);
+    p = fma(p, t, -1.0 / 15.0);
+    p = fma(p, t, 1.0 / 13.0);
+    p = fma(p, t, -1.0 / 11.0);
     p = fma(p, t, 1.0 / 9.0);
     p = fma(p, t, -1.0 / 7.0);
     p = fma(p, t, 1.0 / 5.0);
@@ -145,6 +189,48 @@ __device__ __forceinline__ double tmerc_nav_to_lat(const TMercConst &tm, double 
     sk = sn; ck = cn;
   }
   return phi;
+}
+
+// Same projection, returning sin(lat) and cos(lat) directly (what reference src/PoseUKF.cpp:30 consumes):
+// sin(chi) = sin(xi') / cosh(eta') gives sin/cos(2 chi) algebraically, and lat = chi + eps with the small series sum
+// eps (|eps| < 4e-3) is folded in by the angle-addition formulas -- no asin and only one small-argument sincos.
+__device__ __forceinline__ void tmerc_nav_to_sincos_lat(const TMercConst &tm, double x, double y, double &sin_lat, double &cos_lat) {
+  double xi = x * tm.Ainv + tm.xi0;
+  double eta = -y * tm.Ainv;
+  double s1, c1;
+  sincos(xi, &s1, &c1);
+  double s2 = 2 * s1 * c1, c2 = fma(-2 * s1, s1, 1.0);
+  double e2 = exp(2 * eta), ie2 = fast_rcp(e2);
+  double sh2 = 0.5 * (e2 - ie2), ch2 = 0.5 * (e2 + ie2);
+  double sj = s2, cj = c2, shj = sh2, chj = ch2;
+  double dxi = 0, deta = 0;     // xi' = xi - dxi, eta' = eta - deta
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    dxi = fma(tm.beta[j] * sj, chj, dxi);
+    deta = fma(tm.beta[j] * cj, shj, deta);
+    double sn = sj * c2 + cj * s2, cn = cj * c2 - sj * s2;
+    double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
+    sj = sn; cj = cn; shj = shn; chj = chn;
+  }
+  double sd, cd;
+  sincos(dxi, &sd, &cd);                       // |dxi| < 1e-3
+  double sxp = s1 * cd - c1 * sd;              // sin(xi')
+  double ep = exp(eta - deta);
+  double chp = 0.5 * (ep + fast_rcp(ep));      // cosh(eta')
+  double sch = sxp * fast_rcp(chp);            // sin(chi)
+  double cch = sqrt(fma(-sch, sch, 1.0));      // cos(chi), |chi| < pi/2
+  double sc = 2 * sch * cch, cc = fma(-2 * sch, sch, 1.0);
+  double sk = sc, ck = cc, eps = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    eps = fma(tm.delta[j], sk, eps);
+    double sn = sk * cc + ck * sc, cn = ck * cc - sk * sc;
+    sk = sn; ck = cn;
+  }
+  double se, ce;
+  sincos(eps, &se, &ce);
+  sin_lat = sch * ce + cch * se;
+  cos_lat = cch * ce - sch * se;
 }
 
 // (lat, lon) -> NWU (x, y)   (reference src/PoseUKF.cpp:573 worldToNav)

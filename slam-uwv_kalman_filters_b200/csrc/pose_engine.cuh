@@ -106,7 +106,7 @@ __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double
     for (int j = 0; j < K; ++j) {
       double d = bcast(a[j], j);
       ok = ok && (d > 0.0);
-      double inv = rsqrt(d);
+      double inv = fast_rsqrt(d);
       a[j] = (i == j) ? d * inv : a[j] * inv;
       if (i == j) invd[j] = inv;
 #pragma unroll

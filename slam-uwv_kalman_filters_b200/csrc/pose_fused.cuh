@@ -35,8 +35,17 @@ struct FusedCfg {
   static constexpr int O_L = O_S + PANEL_E;
   static constexpr int O_INVD = O_L + LSZ;
   static constexpr int O_G = O_INVD + KE;          // 3 x KE
-  static constexpr int O_ROWK = O_G + 3 * KE;      // [53][4] = K0 K1 K2 f   (column-side broadcast data)
-  static constexpr int TOTAL = ((O_ROWK + 53 * 4 + 1) / 2) * 2;
+  static constexpr int O_KK = O_G + 3 * KE;        // K rows,      SoA [3][56]
+  static constexpr int O_KS = O_KK + 3 * 56;       // (K S) rows,  SoA [3][56]
+  static constexpr int O_FV = O_KS + 3 * 56;       // diagonal of the affine process map, [56]
+  static constexpr int TOTAL = O_FV + 56;
+  // per-CTA shared region (doubles): packed Q (predict only), index LUT (u16), parameter tables
+  static constexpr int C_Q = 0;
+  static constexpr int C_LUT = HAS_PREDICT ? 1432 : 0;
+  static constexpr int C_FTAB = C_LUT + 360;       // affine factor per tangent index
+  static constexpr int C_MTAU = C_FTAB + 56;       // -1/tau per stored index (0: not a Gauss-Markov state)
+  static constexpr int C_OTAB = C_MTAU + 56;       // shared Markov offsets per stored index (bias offsets)
+  static constexpr int CTA = C_OTAB + 56;
 };
 
 __device__ __forceinline__ int coloff(int j) { return j * N - ((j * (j - 1)) >> 1) - j; }   // cidx(i, j) = coloff(j) + i
@@ -99,18 +108,46 @@ struct RowData {
   double kk[2][3];   // K rows
 };
 
+// -1/tau of stored component s (0 when the process model leaves it alone), reference src/PoseUKF.cpp:37-78
+__device__ inline double markov_rate(int s, const Params &P) {
+  if (s < P_BG) return 0.0;
+  if (s < P_BA) return -1.0 / P.gyro_bias_tau;
+  if (s < P_G) return -1.0 / P.acc_bias_tau;
+  if (s < P_INERTIA) return 0.0;
+  if (s < P_LIN) return -1.0 / P.inertia_tau;
+  if (s < P_QUAD) return -1.0 / P.lin_damping_tau;
+  if (s < P_WV) return -1.0 / P.quad_damping_tau;
+  if (s < P_BADCP) return -1.0 / P.wv_tau;
+  if (s < P_RHO) return -1.0 / P.adcp_bias_tau;
+  return -1.0 / P.rho_tau;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 template <int HAS_PREDICT, int KIND, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P, const uint16_t *__restrict__ lut_g) {
   using C = FusedCfg<HAS_PREDICT, KIND>;
   constexpr int KP = C::KP, KE = C::KE;
   extern __shared__ __align__(16) double smem[];
-  double *Qs = smem;                                 // packed Q (only when HAS_PREDICT)
+  double *Qs = smem + C::C_Q;                        // packed Q (only when HAS_PREDICT)
+  const uint16_t *lut = reinterpret_cast<const uint16_t *>(smem + C::C_LUT);
+  double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *w = smem + (HAS_PREDICT ? 1432 : 0) + warp * C::TOTAL;
-  double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G, *rowK = w + C::O_ROWK;
-  if (HAS_PREDICT) {
-    for (int e = threadIdx.x; e < NP; e += blockDim.x) Qs[e] = a.Q[e];
+  double *w = smem + C::CTA + warp * C::TOTAL;
+  double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G;
+  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *FV = w + C::O_FV;
+  {
+    uint16_t *lw = reinterpret_cast<uint16_t *>(smem + C::C_LUT);
+    for (int e = threadIdx.x; e < NP; e += blockDim.x) {
+      lw[e] = lut_g[e];
+      if (HAS_PREDICT) Qs[e] = a.Q[e];
+    }
+    if (threadIdx.x < 56) {
+      const int t = threadIdx.x;
+      const double dt_ = HAS_PREDICT ? a.ops[0].dt : 0.0;
+      ftab[t] = (HAS_PREDICT && t < N) ? affine_factor(t, P, dt_) : 1.0;
+      mtau[t] = t < DIM ? markov_rate(t, P) : 0.0;
+      otab[t] = (t >= P_BG && t < P_BA) ? P.gyro_bias_offset[t - P_BG] : ((t >= P_BA && t < P_G) ? P.acc_bias_offset[t - P_BA] : 0.0);
+    }
     __syncthreads();
   }
   const Op &op0 = a.ops[0];
@@ -159,9 +196,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           double px = mu[P_POS] + d(0), py = mu[P_POS + 1] + d(1);
           Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
           Vec3 wb{wm_g[0] - (mu[P_BG] + d(12)), wm_g[1] - (mu[P_BG + 1] + d(13)), wm_g[2] - (mu[P_BG + 2] + d(14))};
-          double lat = tmerc_nav_to_lat(P.tm, px, py);
           double sl, cl;
-          sincos(lat, &sl, &cl);
+          tmerc_nav_to_sincos_lat(P.tm, px, py, sl, cl);
           Vec3 wn = qrot(qq, wb);
           wn.x -= kEarthW * cl;
           wn.z -= kEarthW * sl;
@@ -185,11 +221,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
         }
         add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
-        rd.f[0] = affine_factor(x0, P, dt);
-        rd.f[1] = x1 < N ? affine_factor(x1, P, dt) : 1.0;
+        rd.f[0] = ftab[x0];
+        rd.f[1] = ftab[x1 < N ? x1 : N];
+        // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
+        auto new_mean = [&](int sidx_) {
+          const double xv = mu[sidx_];
+          double rate;
+          if (sidx_ < P_ORI) rate = mu[P_VEL + sidx_];
+          else if (sidx_ >= P_VEL && sidx_ < P_ACC) rate = mu[sidx_ + 3];
+          else {
+            const double o = (sidx_ >= P_INERTIA && sidx_ < P_WV) ? off[sidx_ - P_INERTIA] : (sidx_ == P_RHO ? off[27] : otab[sidx_]);
+            rate = mtau[sidx_] * (xv - o);
+          }
+          return xv + dt * rate;
+        };
         double nm0 = 0, nm1 = 0;
-        if (x0 < P_ORI || x0 >= P_VEL) nm0 = affine_mean(x0, mu, off, P, dt);
-        if (x1 < DIM) nm1 = affine_mean(x1, mu, off, P, dt);
+        if (x0 < P_ORI || x0 >= P_VEL) nm0 = new_mean(x0);
+        if (x1 < DIM) nm1 = new_mean(x1);
         __syncwarp();
         // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
         couple3(S, T_POS, T_VEL, dt, lane);
@@ -197,7 +245,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
         for (int b = 0; b < KP; ++b) {
           if (b >= 3 && b < 6) continue;
-          const double fb = affine_factor(b, P, dt);
+          const double fb = ftab[b];
           const int cb = coloff(b);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -365,14 +413,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
-            if (x < N) { rowK[x * 4 + 0] = rd.kk[h][0]; rowK[x * 4 + 1] = rd.kk[h][1]; rowK[x * 4 + 2] = rd.kk[h][2]; }
+            if (x < N) { KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2]; }
           }
           __syncwarp();
           // panel downdate: Sigma[x][b] -= (KS)_x . K_b
 #pragma unroll
           for (int b = 0; b < KP; ++b) {
             const int cb = coloff(b);
-            const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2];
+            const double k0 = KK[b], k1 = KK[56 + b], k2 = KK[112 + b];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
@@ -425,7 +473,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
             for (int b = 0; b < KP; ++b) {
               const int cb = coloff(b);
-              const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2];
+              const double k0 = KK[b], k1 = KK[56 + b], k2 = KK[112 + b];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int x = lane + 32 * h;
@@ -452,79 +500,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
     // =================================== write back ===========================================================
     if (predicted || updated) {
-      // column-side broadcast data for the trailing pass: K_b (zero if no update) and f_b
+      // row tables for the trailing pass: K, K S (zero if no update was applied) and f (one if no predict)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int x = lane + 32 * h;
         if (x < N) {
-          rowK[x * 4 + 0] = rd.kk[h][0]; rowK[x * 4 + 1] = rd.kk[h][1]; rowK[x * 4 + 2] = rd.kk[h][2];
-          rowK[x * 4 + 3] = rd.f[h];
+          KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2];
+          KSs[x] = rd.ks[h][0]; KSs[56 + x] = rd.ks[h][1]; KSs[112 + x] = rd.ks[h][2];
+          FV[x] = rd.f[h];
         }
       }
-      __syncwarp();
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(w);
         constexpr int NV = (56 + C::PANEL_E) / 2;
-        // the last double2 of the staged prefix may straddle the panel end: it was loaded from the block, and the
-        // extra double (first trailing entry) is rewritten by the trailing pass below, which runs after this copy
+        // if PANEL is odd the last double2 also carries the (unchanged) first trailing entry: it is rewritten by the
+        // trailing pass below, which is ordered after this copy by the __syncwarp
 #pragma unroll 4
         for (int k = lane; k < NV; k += 32) __stcs(dst + k, src[k]);
       }
       __syncwarp();
-      // trailing triangle: rows a >= b >= KP, streamed column by column; lane owns rows KP+lane (and KP+32+lane)
+      // trailing triangle (columns >= KP): a contiguous suffix of the packed array, streamed HBM -> registers -> HBM
+      // in flat order (fully coalesced); (row, col) of an entry come from the LUT, row/column factors from the tables
       double *gS = blk + OFF_S;
-      const int a0 = KP + lane, a1 = KP + 32 + lane;
-      // move this lane's row data from "row x = lane / lane+32" ownership to "row KP+lane / KP+32+lane"
-      double fa[2], ksa[2][3];
-      {
-        const int xs0 = a0, xs1 = a1;   // source tangent indices
+      const double q2 = predicted ? dt2 : 0.0;   // FV == 1 and add == 0 unless the predict was applied
+      constexpr int NT = NP - C::PANEL, ROUNDS_T = (NT + 31) / 32, UB = 4;
+      for (int t0 = 0; t0 < ROUNDS_T; t0 += UB) {
+        double v[UB];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int xs = h ? xs1 : xs0;
-          const bool ok = xs < N;
-          const int xr = ok ? xs : 0;
-          fa[h] = ok ? rowK[xr * 4 + 3] : 1.0;
-          // (K S) rows are not in shared memory: fetch them from the owning lane by shuffle
-          const int src_lane = xr & 31, src_h = xr >> 5;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            double v0 = __shfl_sync(kFull, rd.ks[0][c], src_lane), v1 = __shfl_sync(kFull, rd.ks[1][c], src_lane);
-            ksa[h][c] = ok ? (src_h ? v1 : v0) : 0.0;
-          }
-        }
-      }
-      const bool has_a1 = a1 < N;
-      const double q2 = predicted ? dt2 : 0.0;   // rd.f == 1 and add == 0 unless the predict was applied
-      constexpr int CB = 4;                      // columns per batch: all loads of a batch are issued before its stores
-      for (int b0 = KP; b0 < N; b0 += CB) {
-        double v[CB][2];
-#pragma unroll
-        for (int u = 0; u < CB; ++u) {
-          const int b = b0 + u;
-          const int cb = coloff(b);
-          v[u][0] = (b < N && a0 >= b && a0 < N) ? __ldcs(gS + cb + a0) : 0.0;
-          v[u][1] = (b < N && has_a1 && a1 >= b) ? __ldcs(gS + cb + a1) : 0.0;
+        for (int u = 0; u < UB; ++u) {
+          const int e = C::PANEL + lane + 32 * (t0 + u);
+          v[u] = (t0 + u < ROUNDS_T && e < NP) ? __ldcs(gS + e) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < CB; ++u) {
-          const int b = b0 + u;
-          if (b >= N) break;
-          const int cb = coloff(b);
-          const double k0 = rowK[b * 4], k1 = rowK[b * 4 + 1], k2 = rowK[b * 4 + 2], fb = rowK[b * 4 + 3];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ar = h ? a1 : a0;
-            const bool on = h ? (has_a1 && a1 >= b) : (a0 >= b && a0 < N);
-            if (on) {
-              double s = v[u][h];
-              if (HAS_PREDICT) {
-                s = fa[h] * fb * s + q2 * Qs[cb + ar];
-                if (ar == b && b >= T_WV && b < T_BADCP) s += q2 * add;
-              }
-              s = fma(-ksa[h][0], k0, s); s = fma(-ksa[h][1], k1, s); s = fma(-ksa[h][2], k2, s);
-              __stcs(gS + cb + ar, s);
+        for (int u = 0; u < UB; ++u) {
+          const int e = C::PANEL + lane + 32 * (t0 + u);
+          if (t0 + u < ROUNDS_T && e < NP) {
+            const unsigned ij = lut[e];
+            const int ar = ij & 0xff, bc = ij >> 8;
+            double sv = v[u];
+            if (HAS_PREDICT) {
+              sv = FV[ar] * FV[bc] * sv + q2 * Qs[e];
+              if (ar == bc && bc >= T_WV && bc < T_BADCP) sv += q2 * add;
             }
+            if (KIND != M_NONE) {
+              sv = fma(-KSs[ar], KK[bc], sv);
+              sv = fma(-KSs[56 + ar], KK[56 + bc], sv);
+              sv = fma(-KSs[112 + ar], KK[112 + bc], sv);
+            }
+            __stcs(gS + e, sv);
           }
         }
       }

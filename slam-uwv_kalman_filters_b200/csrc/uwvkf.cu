@@ -284,22 +284,24 @@ int launch_pose(uwvkf_handle h, const pose::Launch &L) {
 template <int HP, int KIND>
 constexpr int fused_warps() {
   using C = pose::FusedCfg<HP, KIND>;
-  int w = (232448 - (HP ? 1432 * 8 : 0)) / (C::TOTAL * 8);
+  int w = (232448 - C::CTA * 8) / (C::TOTAL * 8);
   return w > kFusedMaxWarps ? kFusedMaxWarps : w;
 }
 template <int HP, int KIND>
 int launch_fused(uwvkf_handle h, const pose::Launch &L) {
   using C = pose::FusedCfg<HP, KIND>;
   constexpr int WARPS = fused_warps<HP, KIND>();
-  size_t smem = (size_t)((HP ? 1432 : 0) + WARPS * C::TOTAL) * sizeof(double);
+  size_t smem = (size_t)(C::CTA + WARPS * C::TOTAL) * sizeof(double);
   static bool attr_set = false;
+  uint16_t *lut_dev = nullptr;
+  CK(cudaGetSymbolAddress((void **)&lut_dev, g_lut));
   if (!attr_set) {
     CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
-  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
+  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp, lut_dev);
   CK(cudaGetLastError());
   h->launches++;
   return UWVKF_OK;
