@@ -48,6 +48,8 @@ struct FusedCfg {
   static constexpr int CTA = C_OTAB + 56;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ int coloff(int j) { return j * N - ((j * (j - 1)) >> 1) - j; }   // cidx(i, j) = coloff(j) + i
 
 // T[c] = sum_{b<K} G[c][b] * Sigma[b][x] for the two rows x0 = lane, x1 = lane + 32 owned by this lane (registers)
@@ -166,6 +168,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll 4
       for (int k = lane; k < NV; k += 32) dst[k] = __ldcs(src + k);
     }
+    // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
+    // prefix of the warp's next filter into L2 now; also fetch the small per-filter inputs early
+    {
+      const char *tr = reinterpret_cast<const char *>(blk + OFF_S + C::PANEL);
+      constexpr int TB = (NP - C::PANEL) * 8;
+      for (int o = lane * 128; o < TB; o += 32 * 128) prefetch_l2(tr + o);
+      const long long fn = f + (long long)gridDim.x * WARPS;
+      if (fn < a.B) {
+        const char *nx = reinterpret_cast<const char *>(a.state + fn * BLK);
+        constexpr int PB = (56 + C::PANEL_E) * 8;
+        for (int o = lane * 128; o < PB; o += 32 * 128) prefetch_l2(nx + o);
+      }
+    }
+    double off0 = 0.0, off1 = 0.0;
+    if (HAS_PREDICT) {
+      // Markov offsets of the stored components this lane updates (s0 = lane, s1 = lane + 32)
+      const double *off = a.offsets + f * NOFF;
+      const int s0 = lane, s1 = lane + 32;
+      if (s0 >= P_INERTIA) off0 = off[s0 - P_INERTIA];
+      if (s1 < P_WV) off1 = off[s1 - P_INERTIA];
+      else if (s1 == P_RHO) off1 = off[27];
+    }
     __syncwarp();
     unsigned st = 0;
     bool predicted = false, updated = false;
@@ -181,7 +205,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== predict (k = 15) ====================================================
     if constexpr (HAS_PREDICT) {
       constexpr int K = 15;
-      const double *off = a.offsets + f * NOFF;
       const double *wm_g = a.rot_rate + f * 3;
       if (chol_leading<K>(S, Lw, invd, lane)) {
         const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
@@ -224,20 +247,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         rd.f[0] = ftab[x0];
         rd.f[1] = ftab[x1 < N ? x1 : N];
         // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
-        auto new_mean = [&](int sidx_) {
+        auto new_mean = [&](int sidx_, double offv) {
           const double xv = mu[sidx_];
           double rate;
           if (sidx_ < P_ORI) rate = mu[P_VEL + sidx_];
           else if (sidx_ >= P_VEL && sidx_ < P_ACC) rate = mu[sidx_ + 3];
           else {
-            const double o = (sidx_ >= P_INERTIA && sidx_ < P_WV) ? off[sidx_ - P_INERTIA] : (sidx_ == P_RHO ? off[27] : otab[sidx_]);
+            const double o = ((sidx_ >= P_INERTIA && sidx_ < P_WV) || sidx_ == P_RHO) ? offv : otab[sidx_];
             rate = mtau[sidx_] * (xv - o);
           }
           return xv + dt * rate;
         };
         double nm0 = 0, nm1 = 0;
-        if (x0 < P_ORI || x0 >= P_VEL) nm0 = new_mean(x0);
-        if (x1 < DIM) nm1 = new_mean(x1);
+        if (x0 < P_ORI || x0 >= P_VEL) nm0 = new_mean(x0, off0);
+        if (x1 < DIM) nm1 = new_mean(x1, off1);
         __syncwarp();
         // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
         couple3(S, T_POS, T_VEL, dt, lane);
