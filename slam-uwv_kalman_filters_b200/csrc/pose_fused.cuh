@@ -18,9 +18,52 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
+// Measurement traits of the fused kernel: prefix K (tangent coordinates the model reads arbitrarily) plus an AFFINE TAIL
+// of NT consecutive tangent coordinates T0..T0+NT-1 (all >= K) that the model reads affinely once the prefix is fixed.
+// Sigma columns j >= K move only the tail, Z_j(+-) = Z_0 +- C L[T, j], so their sums collapse to Schur complements
+// (tests/structured_ref.py::pose_update_tail states the algebra):
+//   S_zz = 1/2 sum_{centre, j<K} w dz dz^T + C (Sigma_TT - L_T L_T^T) C^T + R,
+//   P_xz = Sigma[:, :K] L11^-T (B - L_T^T C^T) + Sigma[:, T] C^T,         L_T = Sigma[T, :K] L11^-T.
+template <int KIND> struct FMeas : Meas<KIND> {
+  static constexpr int NT = 0, T0 = 0;
+  __device__ static void tail_jac(const double *, const double *, const Params &, double *) {}
+};
+template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, q, gravity) = 19, tail = water density
+  static constexpr int K = 19, M = 1, NT = 1, T0 = T_RHO;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+    Meas<M_PRESSURE>::eval(mu, d, aux, P, o);
+  }
+  __device__ static void tail_jac(const double *mu, const double *aux, const Params &, double *C) {
+    Vec3 rn = qrot(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{aux[0], aux[1], aux[2]});
+    C[0] = -((mu[P_POS + 2] + rn.z) * mu[P_G]);
+  }
+};
+template <> struct FMeas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151: prefix (q, v) = 9, tail = wv, wv_below, bias_adcp
+  static constexpr int K = 9, M = 2, NT = 6, T0 = T_WV;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+    Meas<M_WATER_VELOCITY>::eval(mu, d, aux, P, o);
+  }
+  __device__ static void tail_jac(const double *mu, const double *aux, const Params &, double *C) {   // C[c * NT + r]
+    double Rm[9];
+    qmat(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Rm);
+    const double wgt = aux[0];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {   // (R^T)[c][r] = R[r][c]
+        C[c * 6 + r] = -(1 - wgt) * Rm[r * 3 + c];
+        C[c * 6 + 2 + r] = -wgt * Rm[r * 3 + c];
+        C[c * 6 + 4 + r] = (c == r) ? 1.0 : 0.0;
+      }
+    }
+  }
+};
+
 template <int HAS_PREDICT, int KIND>
 struct FusedCfg {
-  static constexpr int KM = (KIND == M_NONE) ? 0 : Meas<KIND == M_NONE ? M_XY : KIND>::K;   // KIND in {NONE, XY, Z, VELOCITY, ACCELERATION}
+  using MF = FMeas<KIND == M_NONE ? M_XY : KIND>;
+  static constexpr int KM = (KIND == M_NONE) ? 0 : MF::K;
+  static constexpr int NT = (KIND == M_NONE) ? 0 : MF::NT;
   static constexpr int KA = (KIND == M_NONE) ? 0 : 6;                       // apply_delta prefix
   static constexpr int K0 = HAS_PREDICT ? 15 : 0;
   static constexpr int KP = (K0 > KM ? (K0 > KA ? K0 : KA) : (KM > KA ? KM : KA));   // panel width
@@ -38,7 +81,8 @@ struct FusedCfg {
   static constexpr int O_KK = O_G + 3 * KE;        // K rows,      SoA [3][56]
   static constexpr int O_KS = O_KK + 3 * 56;       // (K S) rows,  SoA [3][56]
   static constexpr int O_FV = O_KS + 3 * 56;       // diagonal of the affine process map, [56]
-  static constexpr int TOTAL = O_FV + 56;
+  static constexpr int O_LT = O_FV + 56;           // rows T of the panel factor, NT x KE
+  static constexpr int TOTAL = O_LT + NT * KE;
   // per-CTA shared region (doubles): packed Q (predict only), index LUT (u16), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_LUT = HAS_PREDICT ? 1432 : 0;
@@ -136,7 +180,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G;
-  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *FV = w + C::O_FV;
+  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *FV = w + C::O_FV, *LTs = w + C::O_LT;
+  (void)LTs;
   {
     uint16_t *lw = reinterpret_cast<uint16_t *>(smem + C::C_LUT);
     for (int e = threadIdx.x; e < NP; e += blockDim.x) {
@@ -310,9 +355,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
     // =================================== update (k = Meas::K) + apply_delta (k = 6) ==========================
     if constexpr (KIND != M_NONE) {
-      using MM = Meas<KIND>;
-      constexpr int K = MM::K, M = MM::M;
+      using MM = FMeas<KIND>;
+      constexpr int K = MM::K, M = MM::M, NT = MM::NT, T0 = MM::T0;
       constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
+      static_assert(NT == 0 || (T0 >= C::KP && K <= 32), "the affine tail must lie outside the panel");
+      // entry (ta, tb), ta >= tb >= KP, of the covariance the update works on: the trailing triangle still holds the
+      // pre-predict values in HBM, so the process map is applied on the fly (same expression as the write-back pass)
+      auto trailing = [&](int ta, int tb) {
+        const int e = coloff(tb) + ta;
+        double sv = (blk + OFF_S)[e];
+        if (HAS_PREDICT && predicted) {
+          sv = ftab[ta] * ftab[tb] * sv + dt2 * Qs[HAS_PREDICT ? e : 0];
+          if (ta == tb && tb >= T_WV && tb < T_BADCP) sv += dt2 * add;
+        }
+        return sv;
+      };
       bool go = !(opu.valid && !opu.valid[f]);
       double z[M], Rm[M * M];
       if (go) {
@@ -337,6 +394,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (!chol_leading<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
       }
       if (go) {
+        double lt[NT > 0 ? NT : 1];   // lane j < K: L[T0 + r][j], rows T of the panel factor Sigma[:, :K] L11^-T
+        if constexpr (NT > 0) {
+#pragma unroll
+          for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? S[coloff(lane) + T0 + r] : 0.0;
+          for (int k = 0; k < K; ++k) {   // forward substitution, one column of L11 per step
+            const double ik = invd[k];
+            const double l = (lane > k && lane < K) ? Lw[lidx<K>(lane, k)] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NT; ++r) {
+              const double xk = bcast(lt[r] * ik, k);
+              lt[r] = (lane == k) ? xk : fma(-xk, l, lt[r]);
+            }
+          }
+          if (lane < K) {
+#pragma unroll
+            for (int r = 0; r < NT; ++r) LTs[r * KE + lane] = lt[r];
+          }
+          __syncwarp();
+        }
         double Z[ROUNDS][M], wt[ROUNDS];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
@@ -345,7 +421,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           const bool on = act && p > 0;
           const int j = (p - 1) >> 1;
           const double sg = (p & 1) ? 1.0 : -1.0;
-          auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+          auto d = [&](int t) {
+            if (NT > 0 && t >= K) return on ? sg * LTs[(t - T0) * KE + j] : 0.0;   // t is a literal: resolved at compile time
+            return (on && t >= j) ? sg * Lw[lidx<K>(t < K ? t : 0, j)] : 0.0;
+          };
           MM::eval(mu, d, opu.aux, P, Z[r]);
           wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
         }
@@ -394,9 +473,62 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
         }
         __syncwarp();
+        double Ct[NT > 0 ? M * NT : 1];
+        if constexpr (NT > 0) {
+          MM::tail_jac(mu, opu.aux, P, Ct);
+          // U = C L_T (lane j holds column j); S_zz += C Sigma_TT C^T - U U^T; G <- B - U
+          double U[M];
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            U[c] = 0.0;
+#pragma unroll
+            for (int r = 0; r < NT; ++r) U[c] = fma(Ct[c * NT + r], lt[r], U[c]);
+          }
+          double stt[NT * NT];
+#pragma unroll
+          for (int a2 = 0; a2 < NT; ++a2)
+#pragma unroll
+            for (int b2 = 0; b2 <= a2; ++b2) stt[a2 * NT + b2] = stt[b2 * NT + a2] = trailing(T0 + a2, T0 + b2);
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int b = 0; b <= i; ++b) {
+              double cs = 0;
+#pragma unroll
+              for (int a2 = 0; a2 < NT; ++a2) {
+                double t2 = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < NT; ++b2) t2 = fma(stt[a2 * NT + b2], Ct[b * NT + b2], t2);
+                cs = fma(Ct[i * NT + a2], t2, cs);
+              }
+              const double uu = warp_sum(U[i] * U[b]);
+              Szz[i * M + b] += cs - uu;
+              if (b != i) Szz[b * M + i] += cs - uu;
+            }
+          if (lane < K) {
+#pragma unroll
+            for (int c = 0; c < M; ++c) G[c * KE + lane] -= U[c];
+          }
+          __syncwarp();
+        }
         solve_right<K, M>(G, KE, Lw, invd, lane);
         double T[2][M];
         g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
+        if constexpr (NT > 0) {   // + C Sigma[T, x]: panel columns from shared memory, the rest from the trailing triangle
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int x = lane + 32 * h;
+            if (x < N) {
+#pragma unroll
+              for (int r = 0; r < NT; ++r) {
+                const int t = T0 + r;
+                const double sx = (x < C::KP) ? S[coloff(x) + t] : (x <= t ? trailing(t, x) : trailing(x, t));
+#pragma unroll
+                for (int c = 0; c < M; ++c) T[h][c] = fma(Ct[c * NT + r], sx, T[h][c]);
+              }
+            }
+          }
+        }
         double Si[M * M], nu[M];
         sym_inverse<M>(Szz, Si);
 #pragma unroll
@@ -406,7 +538,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         for (int i = 0; i < M; ++i)
 #pragma unroll
           for (int b = 0; b < M; ++b) d2 += nu[i] * Si[i * M + b] * nu[b];
-        const bool gate95 = (KIND == M_XY) && opu.kind == M_GEOGRAPHIC;   // d2p95, reference src/PoseUKF.cpp:578
+        // d2p95: GeographicPosition (reference src/PoseUKF.cpp:578) and the ADCP update (:610)
+        const bool gate95 = ((KIND == M_XY) && opu.kind == M_GEOGRAPHIC) || KIND == M_WATER_VELOCITY;
         if (gate95 && d2 > 5.991) {
           st |= ST_GATE_REJECTED;
         } else {

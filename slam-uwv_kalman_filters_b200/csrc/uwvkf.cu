@@ -313,11 +313,11 @@ int launch_fused_kind(uwvkf_handle h, const pose::Launch &L, int kind) {
     case UWVKF_POSE_Z: return launch_fused<HP, pose::M_Z>(h, L);
     case UWVKF_POSE_VELOCITY: return launch_fused<HP, pose::M_VELOCITY>(h, L);
     case UWVKF_POSE_ACCELERATION: return launch_fused<HP, pose::M_ACCELERATION>(h, L);
+    case UWVKF_POSE_PRESSURE: return launch_fused<HP, pose::M_PRESSURE>(h, L);
+    case UWVKF_POSE_WATER_VELOCITY: return launch_fused<HP, pose::M_WATER_VELOCITY>(h, L);
   }
   return fail(UWVKF_ERR_INVALID_ARGUMENT, "measurement kind not handled by the fused kernel");
 }
-bool fast_kind(int kind) { return kind != UWVKF_POSE_PRESSURE && kind != UWVKF_POSE_WATER_VELOCITY; }
-
 int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
   pose::Launch L{};
@@ -329,10 +329,11 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
     if (ops[o].type == 0 && !h->have_Q) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_set_process_noise was not called");
     if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_PRESSURE || ops[o].kind == UWVKF_POSE_WATER_VELOCITY)) slow = true;
   }
-  // engine selection: "panel + stream" kernel for predict / fast update / predict+fast update, the resident
-  // kernel for pressure and ADCP (prefix 53 / 52 = dense) and, with UWVKF_ENGINE=v1, for everything (cross-checks)
+  // engine selection: "panel + stream" kernel for predict / update / predict+update (pressure and ADCP through their
+  // affine tail); the resident kernel (dense prefix 53 for pressure / ADCP) for op sequences the fused kernel has no
+  // instantiation for and, with UWVKF_ENGINE=v1, for everything (cross-checks)
   static const bool force_v1 = [] { const char *e = std::getenv("UWVKF_ENGINE"); return e && std::string(e) == "v1"; }();
-  if (!force_v1 && !slow) {
+  if (!force_v1) {
     if (nops == 1 && ops[0].type == 0) return launch_fused<1, pose::M_NONE>(h, L);
     if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
     if (nops == 2 && ops[0].type == 0 && ops[1].type == 1) return launch_fused_kind<1>(h, L, ops[1].kind);

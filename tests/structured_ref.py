@@ -214,3 +214,73 @@ def h_velocity(mu, d):
     q = bplus(mu[3:7], d[3:6])
     v = mu[7:10] + d[6:9]
     return qrot(qconj(q), v)
+
+
+def pose_update_tail(mu, S, z, R, h, k, tail, tail_jac, gate=None, tol=1e-9, max_it=100):
+    """Structured update with an AFFINE TAIL: h reads the first k tangent coordinates arbitrarily
+    and the tangent coordinates `tail` (all >= k) affinely once the prefix is fixed.  Sigma columns j >= k then move only
+    the tail, Z_j(+-) = Z_0 +- C L[tail, j] with C = tail_jac(mu) (m x r), so their sums collapse to Schur complements:
+      S_zz  = 1/2 sum_{centre, j<k} w (Z - zb)(Z - zb)^T + C (Sigma_TT - L_T L_T^T) C^T + R
+      P_xz  = Sigma[:, :k] L11^-T (B - L_T^T C^T) + Sigma[:, T] C^T,        L_T = Sigma[T, :k] L11^-T.
+    h(mu, d, dt): measurement at mu (+) (prefix perturbation d, tail perturbation dt)."""
+    tail = list(tail)
+    L = chol_leading(S, k)
+    LT = np.linalg.solve(L, S[:k, tail]).T  # r x k  (rows `tail` of the full-height panel factor)
+    zero, zt = np.zeros(k), np.zeros(len(tail))
+    Z = [h(mu, zero, zt)] + [h(mu, s * L[:, j], s * LT[:, j]) for j in range(k) for s in (+1, -1)]
+    wts = [1 + 2 * (N - k)] + [1] * (2 * k)
+    ntot = 2 * N + 1
+    zb = Z[0].copy()
+    it = 0
+    while True:
+        m = sum(w * (x - zb) for x, w in zip(Z, wts)) / ntot
+        zb = zb + m
+        it += 1
+        if not (np.linalg.norm(m) > tol and it < max_it):
+            break
+    C = tail_jac(mu)
+    U = C @ LT  # m x k
+    W = C @ S[np.ix_(tail, tail)] @ C.T - U @ U.T
+    Szz = 0.5 * sum(w * np.outer(x - zb, x - zb) for x, w in zip(Z, wts)) + W + R
+    Bm = np.stack([0.5 * (Z[1 + 2 * j] - Z[2 + 2 * j]) for j in range(k)], 1)  # m x k
+    G = np.linalg.solve(L.T, (Bm - U).T).T
+    Pxz = (G @ S[:k, :] + C @ S[tail, :]).T
+    Si = np.linalg.inv(Szz)
+    K = Pxz @ Si
+    nu = z - zb
+    d2 = float(nu @ Si @ nu)
+    if gate is not None and not gate(d2):
+        return mu.copy(), S.copy(), False
+    Sd = S - K @ Szz @ K.T
+    mn, Sn = apply_delta(mu, Sd, K @ nu, tol, max_it)
+    return mn, Sn, True
+
+
+def make_h_pressure(atm_pressure, sensor_in_imu):
+    """reference src/PoseUKF.cpp:107-115: prefix 19 (z, q, gravity), tail = water density (52)."""
+    def h(mu, d, dt):
+        q = bplus(mu[3:7], d[3:6])
+        zn = (mu[2] + d[2]) + qrot(q, sensor_in_imu)[2]
+        return np.array([atm_pressure - zn * (mu[19] + d[18]) * (mu[53] + dt[0])])
+
+    def jac(mu):
+        zn = mu[2] + qrot(mu[3:7], sensor_in_imu)[2]
+        return np.array([[-(zn * mu[19])]])
+    return h, jac
+
+
+def make_h_adcp(wgt):
+    """reference src/PoseUKF.cpp:133-151: prefix 9 (q, v), tail = water velocities and ADCP bias (46..51)."""
+    def h(mu, d, dt):
+        q = bplus(mu[3:7], d[3:6])
+        v = mu[7:10] + d[6:9]
+        wv, wvb, b = mu[47:49] + dt[0:2], mu[49:51] + dt[2:4], mu[51:53] + dt[4:6]
+        qi = qconj(q)
+        below = qrot(qi, v - np.array([wvb[0], wvb[1], 0.0]))
+        around = qrot(qi, v - np.array([wv[0], wv[1], 0.0]))
+        return wgt * below[:2] + (1 - wgt) * around[:2] + b
+
+    def jac(mu):
+        Rt = qmat(mu[3:7]).T[:2, :2]
+        return np.concatenate([-(1 - wgt) * Rt, -wgt * Rt, np.eye(2)], axis=1)
+    return h, jac

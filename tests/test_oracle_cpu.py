@@ -198,6 +198,35 @@ def test_structured_transform_equals_literal_recipe(syn, scen):
             m, c = m3, c3
 
 
+def test_affine_tail_transform_equals_literal_recipe(syn, scen):
+    """Pressure (prefix 19 + tail {water density}) and ADCP (prefix 9 + tail {water velocities, ADCP bias}) evaluated with
+    the affine-tail Schur-complement identities == the literal recipe over all 107 sigma points."""
+    filt = np.array([5, 17])
+    mu, cov = syn.pose_initial_batch(filt, scen["cfg"])
+    par, Q = scen["par"], scen["Q"]
+    for f in range(2):
+        m, c = mu[f], cov[f]
+        off = np.concatenate([m[20:47], m[53:54]])
+        for step in range(1, 5):
+            inp = syn.pose_inputs(filt[f:f + 1], step)
+            w = inp["gyro"][0]
+            m, c, st, _ = orc.pose_predict(m, c, Q, w, par, off, 0.01)
+            m, c, st, _ = orc.pose_update(orc.VELOCITY, m, c, inp["dvl"][0], syn.R_DVL, None, w, par)
+            aux = np.array([0.1, -0.05, 0.2])
+            m1, c1, st, _ = orc.pose_update(orc.PRESSURE, m, c, inp["pressure"][0], syn.R_PRESSURE, aux, w, par)
+            h, jac = sr.make_h_pressure(par[17], aux)
+            m2, c2, ok = sr.pose_update_tail(m, c, inp["pressure"][0], syn.R_PRESSURE, h, 19, [52], jac)
+            assert st == 0 and ok
+            assert np.abs(m2 - m1).max() < 1e-12 * max(1.0, np.abs(m1).max()) and np.abs(c2 - c1).max() < 1e-12 * np.abs(c1).max()
+            wgt = 0.3
+            m3, c3, st, _ = orc.pose_update(orc.WATER_VELOCITY, m1, c1, inp["adcp"][0], syn.R_ADCP, np.array([wgt]), w, par)
+            h, jac = sr.make_h_adcp(wgt)
+            m4, c4, ok = sr.pose_update_tail(m1, c1, inp["adcp"][0], syn.R_ADCP, h, 9, range(46, 52), jac, gate=lambda d2: d2 <= 5.991)
+            assert ok == (st & 4 == 0)
+            assert np.abs(m4 - m3).max() < 1e-12 * max(1.0, np.abs(m3).max()) and np.abs(c4 - c3).max() < 1e-12 * np.abs(c3).max()
+            m, c = m3, c3
+
+
 def test_gate_and_nan_semantics(syn, scen):
     mu, cov = syn.pose_initial(scen["cfg"])
     w = np.zeros(3)

@@ -162,6 +162,35 @@ def test_fused_step_equals_separate_calls(pkg, syn, scen):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("kind", ["pressure", "adcp", "acceleration", "z"])
+def test_fused_predict_update_parity(pkg, syn, scen, kind):
+    """predictionStep + integrateMeasurement(kind) in ONE kernel vs the oracle's two calls.  For pressure / ADCP this
+    exercises the affine tail on a trailing triangle that still holds the pre-predict covariance in HBM."""
+    B = 24
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    inp = syn.pose_inputs(filt, 4)
+    w = inp["gyro"]
+    if kind == "pressure":
+        k, z, R, aux = pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE, np.array([0.3, -0.1, 0.2])
+    elif kind == "adcp":
+        k, z, R, aux = pkg.POSE_WATER_VELOCITY, inp["adcp"], syn.R_ADCP, np.array([0.25])
+    elif kind == "acceleration":
+        k, z, R, aux = pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC, None
+    else:
+        k, z, R, aux = pkg.POSE_Z, np.full((B, 1), syn.truth(4 * DT)["z"]), np.array([[0.0025]]), None
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    ukf.predict_update(DT, w, k, z, R, aux=aux)
+    gmu, gcov = ukf.get_state()
+    omu, ocov = oracle_predict(mu, cov, scen, w, off)
+    omu, ocov, sts = oracle_update(k, omu, ocov, scen, z, R, aux, w)
+    gst = ukf.get_status()
+    assert np.array_equal(gst & 4 != 0, sts & 4 != 0), "gate decisions differ"
+    assert not (gst & ~np.uint32(4)).any()
+    assert_parity(gmu, gcov, omu, ocov, f"fused predict + {kind}")
+    ukf.close()
+
+
 def test_lockstep_sequence_parity(pkg, syn, scen):
     """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
     step so that the asserted error is the per-step error of north_star."""
