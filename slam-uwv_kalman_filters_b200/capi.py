@@ -26,7 +26,8 @@ class UwvkfError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libuwvkf.so")
+    """In-tree CUDA library; UWVKF_LIBRARY selects another build of the same sources (kernel tuning experiments)."""
+    return os.environ.get("UWVKF_LIBRARY") or os.path.join(_HERE, "libuwvkf.so")
 
 
 _lib = None

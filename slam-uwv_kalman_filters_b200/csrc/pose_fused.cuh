@@ -12,6 +12,7 @@
 // shared loads per entry) disappear.
 #pragma once
 #include "pose_engine.cuh"
+#include <type_traits>
 
 namespace uwvkf {
 namespace pose {
@@ -70,7 +71,7 @@ struct FusedCfg {
   static constexpr int PANEL = KP * N - (KP * (KP - 1)) / 2;                // doubles in the panel
   static constexpr int PANEL_E = ((PANEL + 1) / 2) * 2;
   static constexpr int KL = KP;                                             // largest leading factor
-  static constexpr int LSZ = ((KL * (KL + 1) / 2 + 1) / 2) * 2;
+  static constexpr int LSZ = ((KL * (KL | 1) + 1) / 2) * 2;        // square, odd column stride
   static constexpr int KE = ((KL + 1) / 2) * 2;
   // per-warp shared layout (doubles)
   static constexpr int O_MU = 0;                   // 56
@@ -80,13 +81,14 @@ struct FusedCfg {
   static constexpr int O_G = O_INVD + KE;          // 3 x KE
   static constexpr int O_KK = O_G + 3 * KE;        // K rows,      SoA [3][56]
   static constexpr int O_KS = O_KK + 3 * 56;       // (K S) rows,  SoA [3][56]
-  static constexpr int O_FV = O_KS + 3 * 56;       // diagonal of the affine process map, [56]
-  static constexpr int O_LT = O_FV + 56;           // rows T of the panel factor, NT x KE
+  static constexpr int O_LT = O_KS + 3 * 56;           // rows T of the panel factor, NT x KE
   static constexpr int TOTAL = O_LT + NT * KE;
-  // per-CTA shared region (doubles): packed Q (predict only), index LUT (u16), parameter tables
+  // per-CTA shared region (doubles): dt^2 Q packed and the products f_a f_b per packed entry (predict only), the entry ->
+  // (row, column) table as byte offsets into the row tables (u32), parameter tables
   static constexpr int C_Q = 0;
-  static constexpr int C_LUT = HAS_PREDICT ? 1432 : 0;
-  static constexpr int C_FTAB = C_LUT + 360;       // affine factor per tangent index
+  static constexpr int C_FF = HAS_PREDICT ? 1432 : 0;
+  static constexpr int C_LUT = C_FF + (HAS_PREDICT ? 1432 : 0);
+  static constexpr int C_FTAB = C_LUT + 716;       // affine factor per tangent index
   static constexpr int C_MTAU = C_FTAB + 56;       // -1/tau per stored index (0: not a Gauss-Markov state)
   static constexpr int C_OTAB = C_MTAU + 56;       // shared Markov offsets per stored index (bias offsets)
   static constexpr int CTA = C_OTAB + 56;
@@ -95,6 +97,95 @@ struct FusedCfg {
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int coloff(int j) { return j * N - ((j * (j - 1)) >> 1) - j; }   // cidx(i, j) = coloff(j) + i
+
+
+// ---- warp-wide sum on the FP64 tensor path ----------------------------------------------------------------
+// mma.sync.m8n8k4.f64 (SASS DMMA) computes D[i][j] = sum_k A[i][k] B[k][j] with A[i][k] held by lane 4i+k, B[k][j] by lane
+// 4j+k and D[i][2t], D[i][2t+1] by lane 4i+t.  With A = 1 and B = v the first DMMA hands every quad of lanes the eight
+// quad sums of v (two per lane); one DADD and a second DMMA with B = 1 sum those over the quad.  3 instructions and no
+// shuffle instead of 5 x (2 SHFL + DADD): the shuffles of the v2 kernel were 45 % of its shared-memory pipe traffic.
+__device__ __forceinline__ double wsum(double v) {
+  double d0, d1, e0, e1;
+  const double one = 1.0, zero = 0.0;
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(d0), "=d"(d1) : "d"(one), "d"(v), "d"(zero), "d"(zero));
+  const double s = d0 + d1;
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(e0), "=d"(e1) : "d"(s), "d"(one), "d"(zero), "d"(zero));
+  return e0;
+}
+
+// Leading-block Cholesky factor in SQUARE column-major storage with an odd column stride (conflict-free both for
+// "lane = row" and for "lane = column" accesses): L[i][j] = Lw[j * LStride<K> + i].
+template <int K> constexpr int LStride = K | 1;
+
+// Right-looking Cholesky of the leading K x K block (K <= 32): lane i owns row i in registers; the finished column j goes
+// to shared memory (it is needed there anyway) and the other lanes read L[c][j] back as broadcast loads instead of one
+// shuffle pair per entry.  Entries above the diagonal and lanes >= K carry don't-care values that are never consumed.
+template <int K>
+__device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *invd, int lane) {
+  static_assert(K <= 32, "one row per lane");
+  constexpr int LS = LStride<K>;
+  double a[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) a[c] = S[coloff(c) + lane];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const double d = bcast(a[j], j);
+    ok = ok && (d > 0.0);
+    const double inv = fast_rsqrt(d);
+    a[j] *= inv;                          // lane j: d / sqrt(d) = L[j][j]; lanes > j: L[i][j]
+    if (lane < K) Lw[j * LS + lane] = a[j];
+    invd[j] = inv;                        // same value from every lane
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < K; ++c) a[c] = fma(-a[j], Lw[j * LS + c], a[c]);
+  }
+  return ok;
+}
+
+// G <- G L^-1 (G is M x K, row stride gs; lane = column).  Column c is final once steps K-1..c+1 have been applied; its
+// scaling by 1/L[c][c] is folded into the broadcast value, and lane c scales its own entry after the loop, so the loop body
+// has no per-lane special case: M x (DMUL + shuffle pair + DFMA) and one predicated load per column.
+template <int K, int M>
+__device__ __forceinline__ void solve_right_sq(double *G, int gs, const double *Lw, const double *invd, int lane) {
+  constexpr int LS = LStride<K>;
+  double acc[M];
+#pragma unroll
+  for (int r = 0; r < M; ++r) acc[r] = (lane < K) ? G[r * gs + lane] : 0.0;
+#pragma unroll
+  for (int c = K - 1; c > 0; --c) {
+    const double ic = invd[c];
+    const double l = (lane < c) ? Lw[lane * LS + c] : 0.0;
+#pragma unroll
+    for (int r = 0; r < M; ++r) acc[r] = fma(-(bcast(acc[r], c) * ic), l, acc[r]);
+  }
+  if (lane < K) {
+    const double il = invd[lane];
+#pragma unroll
+    for (int r = 0; r < M; ++r) G[r * gs + lane] = acc[r] * il;
+  }
+  __syncwarp();
+}
+
+// equal-weight iterated SO3 mean over 2N+1 logical points, one point (with multiplicity wt) per lane
+__device__ __forceinline__ Quat so3_mean_lane(const Quat &qp, double wt, double tol, int max_it, unsigned &status) {
+  Quat r{bcast(qp.x, 0), bcast(qp.y, 0), bcast(qp.z, 0), bcast(qp.w, 0)};
+  int it = 0;
+  double nrm2;
+  const double tol2 = tol * tol;
+  do {
+    const Vec3 d = so3_boxminus(qp, r);
+    const double mx = wsum(wt * d.x) / double(2 * N + 1);
+    const double my = wsum(wt * d.y) / double(2 * N + 1);
+    const double mz = wsum(wt * d.z) / double(2 * N + 1);
+    r = so3_boxplus(r, Vec3{mx, my, mz}, 1.0);
+    nrm2 = mx * mx + my * my + mz * mz;
+  } while (nrm2 > tol2 && ++it < max_it);
+  if (it >= max_it) status |= ST_MEAN_NOT_CONVERGED;
+  return r;
+}
 
 // T[c] = sum_{b<K} G[c][b] * Sigma[b][x] for the two rows x0 = lane, x1 = lane + 32 owned by this lane (registers)
 template <int K, int M, int KE>
@@ -124,17 +215,16 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
   const bool act = p < 2 * K + 1;
   const bool on = act && p > 0;
   const int j = (p - 1) >> 1;
-  Quat qa[1] = {qp};
-  double wa[1] = {p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0)};
-  Quat r = so3_mean<1>(qa, wa, P.mean_tol, P.mean_max_it, status);
+  const double wa = p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
+  Quat r = so3_mean_lane(qp, wa, P.mean_tol, P.mean_max_it, status);
   Vec3 a = so3_boxminus(qp, r);
-  const double hw = 0.5 * wa[0];
-  soo[0] = warp_sum(hw * a.x * a.x);
-  soo[1] = warp_sum(hw * a.y * a.x);
-  soo[2] = warp_sum(hw * a.z * a.x);
-  soo[3] = warp_sum(hw * a.y * a.y);
-  soo[4] = warp_sum(hw * a.z * a.y);
-  soo[5] = warp_sum(hw * a.z * a.z);
+  const double hw = 0.5 * wa;
+  soo[0] = wsum(hw * a.x * a.x);
+  soo[1] = wsum(hw * a.y * a.x);
+  soo[2] = wsum(hw * a.z * a.x);
+  soo[3] = wsum(hw * a.y * a.y);
+  soo[4] = wsum(hw * a.z * a.y);
+  soo[5] = wsum(hw * a.z * a.z);
   double nx = __shfl_down_sync(kFull, a.x, 1), ny = __shfl_down_sync(kFull, a.y, 1), nz = __shfl_down_sync(kFull, a.z, 1);
   if (on && (p & 1)) {
     G[0 * KE + j] = 0.5 * (a.x - nx);
@@ -142,7 +232,7 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
     G[2 * KE + j] = 0.5 * (a.z - nz);
   }
   __syncwarp();
-  solve_right<K, 3>(G, KE, Lw, invd, lane);
+  solve_right_sq<K, 3>(G, KE, Lw, invd, lane);
   g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
   return r;
 }
@@ -174,26 +264,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   using C = FusedCfg<HAS_PREDICT, KIND>;
   constexpr int KP = C::KP, KE = C::KE;
   extern __shared__ __align__(16) double smem[];
-  double *Qs = smem + C::C_Q;                        // packed Q (only when HAS_PREDICT)
-  const uint16_t *lut = reinterpret_cast<const uint16_t *>(smem + C::C_LUT);
+  double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
+  double *FF = smem + C::C_FF;                       // f_a f_b per packed entry (only when HAS_PREDICT)
+  const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + C::C_LUT);   // (8 row) | (8 col) << 16
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G;
-  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *FV = w + C::O_FV, *LTs = w + C::O_LT;
-  (void)LTs;
+  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *LTs = w + C::O_LT;
+  (void)LTs; (void)FF;
   {
-    uint16_t *lw = reinterpret_cast<uint16_t *>(smem + C::C_LUT);
-    for (int e = threadIdx.x; e < NP; e += blockDim.x) {
-      lw[e] = lut_g[e];
-      if (HAS_PREDICT) Qs[e] = a.Q[e];
-    }
+    const double dt_ = HAS_PREDICT ? a.ops[0].dt : 0.0;
     if (threadIdx.x < 56) {
       const int t = threadIdx.x;
-      const double dt_ = HAS_PREDICT ? a.ops[0].dt : 0.0;
       ftab[t] = (HAS_PREDICT && t < N) ? affine_factor(t, P, dt_) : 1.0;
       mtau[t] = t < DIM ? markov_rate(t, P) : 0.0;
       otab[t] = (t >= P_BG && t < P_BA) ? P.gyro_bias_offset[t - P_BG] : ((t >= P_BA && t < P_G) ? P.acc_bias_offset[t - P_BA] : 0.0);
+    }
+    __syncthreads();
+    uint32_t *lw = reinterpret_cast<uint32_t *>(smem + C::C_LUT);
+    for (int e = threadIdx.x; e < NP; e += blockDim.x) {
+      const unsigned ij = lut_g[e];
+      const unsigned ar = ij & 0xff, bc = ij >> 8;
+      lw[e] = (ar * 8u) | ((bc * 8u) << 16);
+      if (HAS_PREDICT) {
+        Qs[e] = (dt_ * dt_) * a.Q[e];
+        FF[e] = ftab[ar] * ftab[bc];
+      }
     }
     __syncthreads();
   }
@@ -251,14 +348,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     if constexpr (HAS_PREDICT) {
       constexpr int K = 15;
       const double *wm_g = a.rot_rate + f * 3;
-      if (chol_leading<K>(S, Lw, invd, lane)) {
+      if (chol_sq<K>(S, Lw, invd, lane)) {
         const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
         const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};
         const int p = lane;
         const bool on = p > 0 && p < 2 * K + 1;
         const int j = (p - 1) >> 1;
         const double sg = (p & 1) ? 1.0 : -1.0;
-        auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+        auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<K> + t] : 0.0; };
         Quat qp;
         {
           double px = mu[P_POS] + d(0), py = mu[P_POS + 1] + d(1);
@@ -278,6 +375,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         {
           double Rm[9], Qo[9], t[9];
           qmat(q, Rm);
+          // Qs holds dt^2 Q, so qoo comes out scaled as well
           Qo[0] = Qs[cidx(3, 3)]; Qo[1] = Qs[cidx(4, 3)]; Qo[2] = Qs[cidx(5, 3)];
           Qo[3] = Qo[1];          Qo[4] = Qs[cidx(4, 4)]; Qo[5] = Qs[cidx(5, 4)];
           Qo[6] = Qo[2];          Qo[7] = Qo[5];          Qo[8] = Qs[cidx(5, 5)];
@@ -313,12 +411,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
         for (int b = 0; b < KP; ++b) {
           if (b >= 3 && b < 6) continue;
-          const double fb = ftab[b];
           const int cb = coloff(b);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
-            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = rd.f[h] * fb * S[cb + x] + dt2 * Qs[cb + x];
+            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = fma(FF[cb + x], S[cb + x], Qs[cb + x]);
           }
         }
         // orientation rows/cols: T F^T (+ Q cross terms)
@@ -334,14 +431,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
               if (h == 0 && x < 3) tp += dt * t6;
               else if (h == 0 && x >= T_VEL && x < T_ACC) tp += dt * t3;
               const int e = x < 3 ? (coloff(x) + 3 + c) : (coloff(3 + c) + x);
-              S[e] = tp + dt2 * Qs[e];
+              S[e] = tp + Qs[e];
             }
           }
         }
         if (lane < 6) {
           int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
           int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-          S[cidx(3 + bi, 3 + bj)] = soo[lane] + dt2 * qoo[lane];
+          S[cidx(3 + bi, 3 + bj)] = soo[lane] + qoo[lane];
         }
         if (x0 < P_ORI || x0 >= P_VEL) mu[x0] = nm0;
         if (x1 < DIM) mu[x1] = nm1;
@@ -365,7 +462,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         const int e = coloff(tb) + ta;
         double sv = (blk + OFF_S)[e];
         if (HAS_PREDICT && predicted) {
-          sv = ftab[ta] * ftab[tb] * sv + dt2 * Qs[HAS_PREDICT ? e : 0];
+          sv = fma(FF[HAS_PREDICT ? e : 0], sv, Qs[HAS_PREDICT ? e : 0]);
           if (ta == tb && tb >= T_WV && tb < T_BADCP) sv += dt2 * add;
         }
         return sv;
@@ -391,7 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             z[0] = z[0] + (mu[0] - opu.aux[0]); z[1] = z[1] + (mu[1] - opu.aux[1]);
           }
         }
-        if (!chol_leading<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
+        if (!chol_sq<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
       }
       if (go) {
         double lt[NT > 0 ? NT : 1];   // lane j < K: L[T0 + r][j], rows T of the panel factor Sigma[:, :K] L11^-T
@@ -400,7 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? S[coloff(lane) + T0 + r] : 0.0;
           for (int k = 0; k < K; ++k) {   // forward substitution, one column of L11 per step
             const double ik = invd[k];
-            const double l = (lane > k && lane < K) ? Lw[lidx<K>(lane, k)] : 0.0;
+            const double l = (lane > k && lane < K) ? Lw[k * LStride<K> + lane] : 0.0;
 #pragma unroll
             for (int r = 0; r < NT; ++r) {
               const double xk = bcast(lt[r] * ik, k);
@@ -423,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           const double sg = (p & 1) ? 1.0 : -1.0;
           auto d = [&](int t) {
             if (NT > 0 && t >= K) return on ? sg * LTs[(t - T0) * KE + j] : 0.0;   // t is a literal: resolved at compile time
-            return (on && t >= j) ? sg * Lw[lidx<K>(t < K ? t : 0, j)] : 0.0;
+            return (on && t >= j) ? sg * Lw[j * LStride<K> + (t < K ? t : 0)] : 0.0;
           };
           MM::eval(mu, d, opu.aux, P, Z[r]);
           wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
@@ -441,7 +538,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
               double m = 0;
 #pragma unroll
               for (int r = 0; r < ROUNDS; ++r) m = fma(wt[r], Z[r][k] - zb[k], m);
-              m = warp_sum(m) / double(2 * N + 1);
+              m = wsum(m) / double(2 * N + 1);
               zb[k] += m;
               nrm += m * m;
             }
@@ -457,7 +554,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             double s = 0;
 #pragma unroll
             for (int r = 0; r < ROUNDS; ++r) s = fma(0.5 * wt[r] * (Z[r][i] - zb[i]), Z[r][b] - zb[b], s);
-            s = warp_sum(s);
+            s = wsum(s);
             Szz[i * M + b] = s + Rm[i * M + b];
             Szz[b * M + i] = s + Rm[b * M + i];
           }
@@ -501,7 +598,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
                 for (int b2 = 0; b2 < NT; ++b2) t2 = fma(stt[a2 * NT + b2], Ct[b * NT + b2], t2);
                 cs = fma(Ct[i * NT + a2], t2, cs);
               }
-              const double uu = warp_sum(U[i] * U[b]);
+              const double uu = wsum(U[i] * U[b]);
               Szz[i * M + b] += cs - uu;
               if (b != i) Szz[b * M + i] += cs - uu;
             }
@@ -511,7 +608,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
           __syncwarp();
         }
-        solve_right<K, M>(G, KE, Lw, invd, lane);
+        solve_right_sq<K, M>(G, KE, Lw, invd, lane);
         double T[2][M];
         g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
         if constexpr (NT > 0) {   // + C Sigma[T, x]: panel columns from shared memory, the rest from the trailing triangle
@@ -592,14 +689,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           __syncwarp();
           // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
           constexpr int KA = 6;
-          if (chol_leading<KA>(S, Lw, invd, lane)) {
+          if (chol_sq<KA>(S, Lw, invd, lane)) {
             const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
             const double d3 = bcast(dl[0], 3), d4 = bcast(dl[0], 4), d5 = bcast(dl[0], 5);
             const int p = lane;
             const bool on = p > 0 && p < 2 * KA + 1;
             const int j = (p - 1) >> 1;
             const double sg = (p & 1) ? 1.0 : -1.0;
-            auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<KA>(t, j)] : 0.0; };
+            auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<KA> + t] : 0.0; };
             Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
             double soo[6], TA[2][3];
             Quat r = ori_transform_reg<KA, KE>(S, Lw, invd, G, qp, p, P, soo, TA, lane, st);
@@ -656,14 +753,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
     // =================================== write back ===========================================================
     if (predicted || updated) {
-      // row tables for the trailing pass: K, K S (zero if no update was applied) and f (one if no predict)
+      // row tables for the trailing pass: K and K S (zero if no update was applied)
+      if (KIND != M_NONE) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int x = lane + 32 * h;
-        if (x < N) {
-          KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2];
-          KSs[x] = rd.ks[h][0]; KSs[56 + x] = rd.ks[h][1]; KSs[112 + x] = rd.ks[h][2];
-          FV[x] = rd.f[h];
+        for (int h = 0; h < 2; ++h) {
+          const int x = lane + 32 * h;
+          if (x < N) {
+            KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2];
+            KSs[x] = rd.ks[h][0]; KSs[56 + x] = rd.ks[h][1]; KSs[112 + x] = rd.ks[h][2];
+          }
         }
       }
       {
@@ -676,38 +774,52 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         for (int k = lane; k < NV; k += 32) __stcs(dst + k, src[k]);
       }
       __syncwarp();
-      // trailing triangle (columns >= KP): a contiguous suffix of the packed array, streamed HBM -> registers -> HBM
-      // in flat order (fully coalesced); (row, col) of an entry come from the LUT, row/column factors from the tables
+      // trailing triangle (columns >= KP): a contiguous suffix of the packed array, streamed HBM -> registers -> HBM in flat
+      // order (fully coalesced):  s <- (f_a f_b) s + dt^2 Q_ab - sum_c (K S)_ac K_bc.  f_a f_b and dt^2 Q come from per-CTA
+      // tables indexed like the entry, the row/column offsets into the K tables from the LUT; the four water-velocity diagonal
+      // entries that also receive the velocity-dependent noise sit at compile-time (round, lane) positions.
       double *gS = blk + OFF_S;
-      const double q2 = predicted ? dt2 : 0.0;   // FV == 1 and add == 0 unless the predict was applied
-      constexpr int NT = NP - C::PANEL, ROUNDS_T = (NT + 31) / 32, UB = 4;
-      for (int t0 = 0; t0 < ROUNDS_T; t0 += UB) {
-        double v[UB];
+      constexpr int NTR = NP - C::PANEL, ROUNDS_T = (NTR + 31) / 32, UB = 8;
+      const double q2add = dt2 * add;
+      auto pass = [&](auto apply_predict) {
+        constexpr bool AP = decltype(apply_predict)::value;
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int e = C::PANEL + lane + 32 * (t0 + u);
-          v[u] = (t0 + u < ROUNDS_T && e < NP) ? __ldcs(gS + e) : 0.0;
-        }
+        for (int t0 = 0; t0 < ROUNDS_T; t0 += UB) {
+          double v[UB];
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int e = C::PANEL + lane + 32 * (t0 + u);
-          if (t0 + u < ROUNDS_T && e < NP) {
-            const unsigned ij = lut[e];
-            const int ar = ij & 0xff, bc = ij >> 8;
-            double sv = v[u];
-            if (HAS_PREDICT) {
-              sv = FV[ar] * FV[bc] * sv + q2 * Qs[e];
-              if (ar == bc && bc >= T_WV && bc < T_BADCP) sv += q2 * add;
+          for (int u = 0; u < UB; ++u) {
+            const int t = t0 + u, e = C::PANEL + lane + 32 * t;
+            if (t < ROUNDS_T) v[u] = (t < ROUNDS_T - 1 || e < NP) ? __ldcs(gS + e) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int t = t0 + u, e = C::PANEL + lane + 32 * t;
+            if (t < ROUNDS_T && (t < ROUNDS_T - 1 || e < NP)) {
+              double sv = v[u];
+              if (AP) {
+                sv = fma(FF[e], sv, Qs[e]);
+#pragma unroll
+                for (int dg = T_WV; dg < T_BADCP; ++dg) {
+                  constexpr int dummy = 0; (void)dummy;
+                  const int ed = cidx(dg, dg) - C::PANEL;      // folds to a constant once the loops are unrolled
+                  if (t == ed / 32 && lane == ed % 32) sv += q2add;
+                }
+              }
+              if (KIND != M_NONE) {
+                const unsigned ij = lut[e];
+                const char *kr = reinterpret_cast<const char *>(KSs) + (ij & 0xffffu);
+                const char *kc = reinterpret_cast<const char *>(KK) + (ij >> 16);
+                sv = fma(-*reinterpret_cast<const double *>(kr), *reinterpret_cast<const double *>(kc), sv);
+                sv = fma(-*reinterpret_cast<const double *>(kr + 448), *reinterpret_cast<const double *>(kc + 448), sv);
+                sv = fma(-*reinterpret_cast<const double *>(kr + 896), *reinterpret_cast<const double *>(kc + 896), sv);
+              }
+              __stcs(gS + e, sv);
             }
-            if (KIND != M_NONE) {
-              sv = fma(-KSs[ar], KK[bc], sv);
-              sv = fma(-KSs[56 + ar], KK[56 + bc], sv);
-              sv = fma(-KSs[112 + ar], KK[112 + bc], sv);
-            }
-            __stcs(gS + e, sv);
           }
         }
-      }
+      };
+      if (HAS_PREDICT && predicted) pass(std::true_type{});
+      else pass(std::false_type{});
     }
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();

@@ -204,7 +204,10 @@ int small_ensemble_stats(uwvkf_handle h, double *dout) {
 // ======================================================================================================
 namespace {
 
-constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = 16;
+#ifndef UWVKF_FUSED_MAX_WARPS
+#define UWVKF_FUSED_MAX_WARPS 12
+#endif
+constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
 }  // namespace
