@@ -196,6 +196,20 @@ int uwvkf_indirect_update_features(uwvkf_handle h, int nfeat, const double *px, 
 /* getCorrectedPose (:137-142): out[B][7], host */
 int uwvkf_indirect_get_corrected_pose(uwvkf_handle h, double *out);
 
+/* ---- device-math probe (tests only) ------------------------------------------------------------------- */
+/* Evaluates one device function of the engine per input row on the GPU so that tests can pin the kernels' math against
+ * the oracle / high-precision values: in[n][8] -> out[n][4] (host pointers, PoseUKF handle with parameters set).
+ *   TMERC_SINCOS_LAT  in = x, y [m, NWU]           out = sin(lat), cos(lat) (fast path), lat (generic path)
+ *   SO3_BOXPLUS       in = q(x,y,z,w), v(3), scale out = q (+) scale*v
+ *   SO3_BOXMINUS      in = a(x,y,z,w), b(x,y,z,w)  out = a (-) b
+ *   RSQRT             in = d                       out = 1/sqrt(d) (third-order), 1/sqrt(d) (two Newton steps), 1/d
+ *   WARP_SUM          in = v                       out = sum of v over the 32 rows of the same warp (DMMA path, shuffle path) */
+enum uwvkf_debug_what {
+  UWVKF_DEBUG_TMERC_SINCOS_LAT = 0, UWVKF_DEBUG_SO3_BOXPLUS = 1, UWVKF_DEBUG_SO3_BOXMINUS = 2, UWVKF_DEBUG_RSQRT = 3,
+  UWVKF_DEBUG_WARP_SUM = 4
+};
+int uwvkf_debug_eval(uwvkf_handle h, int what, const double *in, double *out, int n);
+
 /* ---- ensemble statistics (north_star: the only cross-GPU exchange) -------------------------------- */
 /* Writes [count, sum mu (DIM), sum mu mu^T lower triangle row-major (DIM*(DIM+1)/2)] over this handle's filters into
  * out (device or host pointer, 1 + DIM + DIM*(DIM+1)/2 doubles).  The caller all-reduces it (NCCL sum). */

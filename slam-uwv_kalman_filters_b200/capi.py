@@ -67,6 +67,7 @@ def load_library():
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_debug_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         vp, ci = C.c_void_p, C.c_int
         lib.uwvkf_velocity_setup_motion_model.argtypes = [vp, vp]
         lib.uwvkf_velocity_set_gyro.argtypes = [vp, vp, ci]
@@ -330,6 +331,16 @@ class PoseUKFBatch(_FilterBatch):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_predict_update(self._h, float(dt), _ptr(w), kind, _ptr(z), _ptr(R), per, _ptr(aux),
                                                      _ptr(valid), memspace))
+
+    DEBUG_TMERC_SINCOS_LAT, DEBUG_SO3_BOXPLUS, DEBUG_SO3_BOXMINUS, DEBUG_RSQRT, DEBUG_WARP_SUM = range(5)
+
+    def debug_eval(self, what, rows):
+        """Device-math probe (tests): evaluates one device function per input row, rows [n, 8] -> [n, 4]."""
+        rows = _f64(rows)
+        assert rows.ndim == 2 and rows.shape[1] == 8
+        out = np.empty((rows.shape[0], 4))
+        self._ck(self._lib.uwvkf_debug_eval(self._h, int(what), _ptr(rows), _ptr(out), rows.shape[0]))
+        return out
 
     def reset_with_external_pose(self, pose7):
         """resetFilterWithExternalPose (src/PoseUKF.cpp:685-691)."""

@@ -32,6 +32,45 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
   y = fma(0.5 * y, e, y);
   return y;
 }
+// same result (seed error 2^-22 cubed per step), one third-order step: y (1 + e/2 + 3 e^2 / 8), e = 1 - d y^2
+__device__ __forceinline__ double fast_rsqrt3(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+
+// sin and cos of a SMALL argument (|x| <= 2^-4) by their Taylor polynomials (truncation < 3e-19 relative): what libm
+// returns to an ulp, without its argument reduction.  Callers guard the range and fall back to sincos().
+__device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
+  const double u = x * x;
+  double ps = fma(u, 1.0 / 362880.0, -1.0 / 5040.0);
+  ps = fma(ps, u, 1.0 / 120.0);
+  ps = fma(ps, u, -1.0 / 6.0);
+  sn = fma(x * u, ps, x);
+  double pc = fma(u, -1.0 / 3628800.0, 1.0 / 40320.0);
+  pc = fma(pc, u, -1.0 / 720.0);
+  pc = fma(pc, u, 1.0 / 24.0);
+  pc = fma(pc, u, -0.5);
+  cs = fma(pc, u, 1.0);
+}
+// sinh and cosh of a small argument (|t| <= 2^-3), Taylor (truncation < 4e-20 relative); no cancellation near 0
+__device__ __forceinline__ void sinhcosh_small(double t, double &sh, double &ch) {
+  const double u = t * t;
+  double ps = fma(u, 1.0 / 39916800.0, 1.0 / 362880.0);
+  ps = fma(ps, u, 1.0 / 5040.0);
+  ps = fma(ps, u, 1.0 / 120.0);
+  ps = fma(ps, u, 1.0 / 6.0);
+  sh = fma(t * u, ps, t);
+  double pc = fma(u, 1.0 / 479001600.0, 1.0 / 3628800.0);
+  pc = fma(pc, u, 1.0 / 40320.0);
+  pc = fma(pc, u, 1.0 / 720.0);
+  pc = fma(pc, u, 1.0 / 24.0);
+  pc = fma(pc, u, 0.5);
+  ch = fma(pc, u, 1.0);
+}
 // 1/x (normal range): seed + two Newton steps
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
@@ -156,6 +195,7 @@ __device__ __forceinline__ Vec3 so3_boxminus(const Quat &a, const Quat &b) { ret
 // ---- local transverse Mercator (Krueger series, order n^6); constants are filled on the host -----
 struct TMercConst {
   double lat0, lon0, A, Ainv, xi0, e;
+  double sin_xi0, cos_xi0;
   double alpha[6], beta[6], delta[6];
 };
 
@@ -195,13 +235,25 @@ __device__ __forceinline__ double tmerc_nav_to_lat(const TMercConst &tm, double 
 // sin(chi) = sin(xi') / cosh(eta') gives sin/cos(2 chi) algebraically, and lat = chi + eps with the small series sum
 // eps (|eps| < 4e-3) is folded in by the angle-addition formulas -- no asin and only one small-argument sincos.
 __device__ __forceinline__ void tmerc_nav_to_sincos_lat(const TMercConst &tm, double x, double y, double &sin_lat, double &cos_lat) {
-  double xi = x * tm.Ainv + tm.xi0;
+  const double dx = x * tm.Ainv;
+  double xi = dx + tm.xi0;
   double eta = -y * tm.Ainv;
-  double s1, c1;
-  sincos(xi, &s1, &c1);
+  // within ~400 km of the projection origin every transcendental argument is small: Taylor polynomials around the origin
+  // (sin/cos(xi0) come from the host) replace sincos / exp; outside that range the generic routines are used
+  const bool near = fabs(dx) <= 0.0625 && fabs(eta) <= 0.0625;
+  double s1, c1, sh2, ch2;
+  if (near) {
+    double sd_, cd_;
+    sincos_small(dx, sd_, cd_);
+    s1 = fma(tm.sin_xi0, cd_, tm.cos_xi0 * sd_);
+    c1 = fma(tm.cos_xi0, cd_, -(tm.sin_xi0 * sd_));
+    sinhcosh_small(2 * eta, sh2, ch2);
+  } else {
+    sincos(xi, &s1, &c1);
+    double e2 = exp(2 * eta), ie2 = fast_rcp(e2);
+    sh2 = 0.5 * (e2 - ie2); ch2 = 0.5 * (e2 + ie2);
+  }
   double s2 = 2 * s1 * c1, c2 = fma(-2 * s1, s1, 1.0);
-  double e2 = exp(2 * eta), ie2 = fast_rcp(e2);
-  double sh2 = 0.5 * (e2 - ie2), ch2 = 0.5 * (e2 + ie2);
   double sj = s2, cj = c2, shj = sh2, chj = ch2;
   double dxi = 0, deta = 0;     // xi' = xi - dxi, eta' = eta - deta
 #pragma unroll
@@ -212,11 +264,17 @@ __device__ __forceinline__ void tmerc_nav_to_sincos_lat(const TMercConst &tm, do
     double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
     sj = sn; cj = cn; shj = shn; chj = chn;
   }
-  double sd, cd;
-  sincos(dxi, &sd, &cd);                       // |dxi| < 1e-3
+  double sd, cd, chp;
+  if (near && fabs(dxi) <= 0.0625) {
+    double shp;
+    sincos_small(dxi, sd, cd);                   // |dxi| < 1e-3
+    sinhcosh_small(eta - deta, shp, chp);        // cosh(eta')
+  } else {
+    sincos(dxi, &sd, &cd);
+    double ep = exp(eta - deta);
+    chp = 0.5 * (ep + fast_rcp(ep));
+  }
   double sxp = s1 * cd - c1 * sd;              // sin(xi')
-  double ep = exp(eta - deta);
-  double chp = 0.5 * (ep + fast_rcp(ep));      // cosh(eta')
   double sch = sxp * fast_rcp(chp);            // sin(chi)
   double cch = sqrt(fma(-sch, sch, 1.0));      // cos(chi), |chi| < pi/2
   double sc = 2 * sch * cch, cc = fma(-2 * sch, sch, 1.0);
@@ -228,7 +286,8 @@ __device__ __forceinline__ void tmerc_nav_to_sincos_lat(const TMercConst &tm, do
     sk = sn; ck = cn;
   }
   double se, ce;
-  sincos(eps, &se, &ce);
+  if (fabs(eps) <= 0.0625) sincos_small(eps, se, ce);   // |eps| < 4e-3
+  else sincos(eps, &se, &ce);
   sin_lat = sch * ce + cch * se;
   cos_lat = cch * ce - sch * se;
 }

@@ -134,7 +134,7 @@ __device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *inv
   for (int j = 0; j < K; ++j) {
     const double d = bcast(a[j], j);
     ok = ok && (d > 0.0);
-    const double inv = fast_rsqrt(d);
+    const double inv = fast_rsqrt3(d);
     a[j] *= inv;                          // lane j: d / sqrt(d) = L[j][j]; lanes > j: L[i][j]
     if (lane < K) Lw[j * LS + lane] = a[j];
     invd[j] = inv;                        // same value from every lane
@@ -177,9 +177,10 @@ __device__ __forceinline__ Quat so3_mean_lane(const Quat &qp, double wt, double 
   const double tol2 = tol * tol;
   do {
     const Vec3 d = so3_boxminus(qp, r);
-    const double mx = wsum(wt * d.x) / double(2 * N + 1);
-    const double my = wsum(wt * d.y) / double(2 * N + 1);
-    const double mz = wsum(wt * d.z) / double(2 * N + 1);
+    constexpr double kInvPts = 1.0 / double(2 * N + 1);   // mean over the 2n+1 points (one rounding away from a division)
+    const double mx = wsum(wt * d.x) * kInvPts;
+    const double my = wsum(wt * d.y) * kInvPts;
+    const double mz = wsum(wt * d.z) * kInvPts;
     r = so3_boxplus(r, Vec3{mx, my, mz}, 1.0);
     nrm2 = mx * mx + my * my + mz * mz;
   } while (nrm2 > tol2 && ++it < max_it);
@@ -235,6 +236,38 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
   solve_right_sq<K, 3>(G, KE, Lw, invd, lane);
   g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
   return r;
+}
+
+// In-place congruence Sigma <- C Sigma C^T with C = I + dt E(rows D0.. <- rows S0..) on 3 consecutive rows (same result as
+// couple3 in pose_engine.cuh).  Row / column indices known at compile time give constant column offsets; only the
+// lane-dependent side of an entry needs coloff(lane), which the caller hoists out of the filter loop.
+template <int D0, int S0>
+__device__ __forceinline__ void couple3_f(double *S, double dt, int lane, int colane) {
+  auto pidx = [&](int fixed, int b, int cob) { return (b >= fixed) ? coloff(fixed) + b : cob + fixed; };
+  double nb = 0.0;
+  int eb = 0;
+  if (lane < 6) {
+    const int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
+    const int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
+    eb = cidx(D0 + bi, D0 + bj);
+    nb = S[eb] + dt * (S[sidx(S0 + bi, D0 + bj)] + S[sidx(D0 + bi, S0 + bj)]) + dt * dt * S[sidx(S0 + bi, S0 + bj)];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int b = lane + 32 * h;
+    const int cob = h ? coloff(b) : colane;
+    if (b < N && (b < D0 || b >= D0 + 3)) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ed = pidx(D0 + i, b, cob), es = pidx(S0 + i, b, cob);
+        S[ed] = fma(dt, S[es], S[ed]);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < 6) S[eb] = nb;
+  __syncwarp();
 }
 
 // per-lane row data for the rows x0 = lane and x1 = lane + 32
@@ -299,6 +332,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const double dt = HAS_PREDICT ? op0.dt : 0.0;
   const double dt2 = dt * dt;
   const int x0 = lane, x1 = lane + 32;
+  const int colane = coloff(lane);
+  (void)colane;
 
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
@@ -335,13 +370,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     __syncwarp();
     unsigned st = 0;
     bool predicted = false, updated = false;
-    RowData rd;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      rd.f[h] = 1.0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { rd.ks[h][c] = 0.0; rd.kk[h][c] = 0.0; }
-    }
     double add = 0.0;
 
     // =================================== predict (k = 15) ====================================================
@@ -387,8 +415,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
         }
         add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
-        rd.f[0] = ftab[x0];
-        rd.f[1] = ftab[x1 < N ? x1 : N];
+        const double rdf[2] = {ftab[x0], ftab[x1 < N ? x1 : N]};
         // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
         auto new_mean = [&](int sidx_, double offv) {
           const double xv = mu[sidx_];
@@ -406,8 +433,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (x1 < DIM) nm1 = new_mean(x1, off1);
         __syncwarp();
         // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
-        couple3(S, T_POS, T_VEL, dt, lane);
-        couple3(S, T_VEL, T_ACC, dt, lane);
+        couple3_f<T_POS, T_VEL>(S, dt, lane, colane);
+        couple3_f<T_VEL, T_ACC>(S, dt, lane, colane);
 #pragma unroll
         for (int b = 0; b < KP; ++b) {
           if (b >= 3 && b < 6) continue;
@@ -427,7 +454,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             // coupled partner: T[c][x+6] for x in pos, T[c][x+3] for x in vel (both in round 0)
             double t6 = __shfl_sync(kFull, T[0][c], (lane + 6) & 31), t3 = __shfl_sync(kFull, T[0][c], (lane + 3) & 31);
             if (x < N && !(x >= 3 && x < 6)) {
-              double tp = rd.f[h] * T[h][c];
+              double tp = rdf[h] * T[h][c];
               if (h == 0 && x < 3) tp += dt * t6;
               else if (h == 0 && x >= T_VEL && x < T_ACC) tp += dt * t3;
               const int e = x < 3 ? (coloff(x) + 3 + c) : (coloff(3 + c) + x);
@@ -538,12 +565,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
               double m = 0;
 #pragma unroll
               for (int r = 0; r < ROUNDS; ++r) m = fma(wt[r], Z[r][k] - zb[k], m);
-              m = wsum(m) / double(2 * N + 1);
+              m = wsum(m) * (1.0 / double(2 * N + 1));
               zb[k] += m;
               nrm += m * m;
             }
-            nrm = sqrt(nrm);
-          } while (nrm > P.mean_tol && ++it < P.mean_max_it);
+          } while (nrm > P.mean_tol * P.mean_tol && ++it < P.mean_max_it);   // nrm holds the squared norm
           if (it >= P.mean_max_it) st |= ST_MEAN_NOT_CONVERGED;
         }
         double Szz[M * M];
@@ -640,8 +666,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (gate95 && d2 > 5.991) {
           st |= ST_GATE_REJECTED;
         } else {
-          // gain rows, (K S) rows and delta for the rows this lane owns
-          double dl[2];
+          // gain rows, (K S) rows and delta for the rows this lane owns; K and K S go straight to the row tables the
+          // trailing pass reads (and are re-read from there in the rare rollback) so that they do not stay in registers
+          double dl[2], kk[2][3] = {{0, 0, 0}, {0, 0, 0}}, ks[2][3] = {{0, 0, 0}, {0, 0, 0}};
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             double dx = 0;
@@ -650,15 +677,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
               double s = 0;
 #pragma unroll
               for (int c = 0; c < M; ++c) s += T[h][c] * Si[c * M + i];
-              rd.kk[h][i] = s;
+              kk[h][i] = s;
               dx += s * nu[i];
             }
 #pragma unroll
             for (int i = 0; i < M; ++i) {
               double s = 0;
 #pragma unroll
-              for (int c = 0; c < M; ++c) s += rd.kk[h][c] * Szz[c * M + i];
-              rd.ks[h][i] = s;
+              for (int c = 0; c < M; ++c) s += kk[h][c] * Szz[c * M + i];
+              ks[h][i] = s;
             }
             dl[h] = dx;
           }
@@ -666,7 +693,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
-            if (x < N) { KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2]; }
+            if (x < N) {
+              KK[x] = kk[h][0]; KK[56 + x] = kk[h][1]; KK[112 + x] = kk[h][2];
+              KSs[x] = ks[h][0]; KSs[56 + x] = ks[h][1]; KSs[112 + x] = ks[h][2];
+            }
           }
           __syncwarp();
           // panel downdate: Sigma[x][b] -= (KS)_x . K_b
@@ -679,9 +709,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
               const int x = lane + 32 * h;
               if (x >= b && x < N) {
                 double s = S[cb + x];
-                s = fma(-rd.ks[h][0], k0, s);
-                if (M > 1) s = fma(-rd.ks[h][1], k1, s);
-                if (M > 2) s = fma(-rd.ks[h][2], k2, s);
+                s = fma(-ks[h][0], k0, s);
+                if (M > 1) s = fma(-ks[h][1], k1, s);
+                if (M > 2) s = fma(-ks[h][2], k2, s);
                 S[cb + x] = s;
               }
             }
@@ -732,9 +762,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
                 const int x = lane + 32 * h;
                 if (x >= b && x < N) {
                   double s = S[cb + x];
-                  s = fma(rd.ks[h][0], k0, s);
-                  if (M > 1) s = fma(rd.ks[h][1], k1, s);
-                  if (M > 2) s = fma(rd.ks[h][2], k2, s);
+                  s = fma(KSs[x], k0, s);
+                  if (M > 1) s = fma(KSs[56 + x], k1, s);
+                  if (M > 2) s = fma(KSs[112 + x], k2, s);
                   S[cb + x] = s;
                 }
               }
@@ -743,27 +773,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
         }
       }
-      if (!updated) {
+      if (!updated && predicted) {   // the trailing pass below then applies the process map only: K = K S = 0
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          const int x = lane + 32 * h;
+          if (x < N) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) { rd.ks[h][c] = 0.0; rd.kk[h][c] = 0.0; }
+            for (int c = 0; c < 3; ++c) { KK[56 * c + x] = 0.0; KSs[56 * c + x] = 0.0; }
+          }
+        }
       }
     }
 
     // =================================== write back ===========================================================
     if (predicted || updated) {
-      // row tables for the trailing pass: K and K S (zero if no update was applied)
-      if (KIND != M_NONE) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int x = lane + 32 * h;
-          if (x < N) {
-            KK[x] = rd.kk[h][0]; KK[56 + x] = rd.kk[h][1]; KK[112 + x] = rd.kk[h][2];
-            KSs[x] = rd.ks[h][0]; KSs[56 + x] = rd.ks[h][1]; KSs[112 + x] = rd.ks[h][2];
-          }
-        }
-      }
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(w);

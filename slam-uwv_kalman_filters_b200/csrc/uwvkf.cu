@@ -151,6 +151,22 @@ __global__ void pose_rotation_rate_kernel(const double *state, const double *rot
   out[f * 3 + 2] = rot_rate[f * 3 + 2] - mu[pose::P_BG + 2] - eb.z;
 }
 
+// device-math probe (uwvkf_debug_eval): one evaluation per thread, inputs in[n][8] -> out[n][4]
+__global__ void debug_eval_kernel(int what, const double *in, double *out, int n, const __grid_constant__ pose::Params P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < n;
+  const double *a = in + (size_t)(act ? i : 0) * 8;
+  double o[4] = {0, 0, 0, 0};
+  switch (what) {
+    case UWVKF_DEBUG_TMERC_SINCOS_LAT: tmerc_nav_to_sincos_lat(P.tm, a[0], a[1], o[0], o[1]); o[2] = tmerc_nav_to_lat(P.tm, a[0], a[1]); break;
+    case UWVKF_DEBUG_SO3_BOXPLUS: { Quat q = so3_boxplus(Quat{a[0], a[1], a[2], a[3]}, Vec3{a[4], a[5], a[6]}, a[7]); o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; break; }
+    case UWVKF_DEBUG_SO3_BOXMINUS: { Vec3 v = so3_boxminus(Quat{a[0], a[1], a[2], a[3]}, Quat{a[4], a[5], a[6], a[7]}); o[0] = v.x; o[1] = v.y; o[2] = v.z; break; }
+    case UWVKF_DEBUG_RSQRT: o[0] = fast_rsqrt3(a[0]); o[1] = fast_rsqrt(a[0]); o[2] = fast_rcp(a[0]); break;
+    case UWVKF_DEBUG_WARP_SUM: o[0] = pose::wsum(act ? a[0] : 0.0); o[1] = warp_sum(act ? a[0] : 0.0); break;   // sums over each warp
+  }
+  if (act) for (int k = 0; k < 4; ++k) out[(size_t)i * 4 + k] = o[k];
+}
+
 // ensemble statistics: out = [count, sum mu (DIM), sum mu mu^T (lower, row-major packed)]
 template <int DIM>
 __global__ void ensemble_stats_kernel(const double *state, long long stride, long long B, double *out) {
@@ -255,6 +271,8 @@ void fill_tmerc(TMercConst &tm, double lat0, double lon0) {
   double chi0 = std::atan(taup), s = chi0;
   for (int j = 0; j < 6; ++j) s += al[j] * std::sin(2 * (j + 1) * chi0);
   tm.xi0 = s;
+  tm.sin_xi0 = std::sin(s);
+  tm.cos_xi0 = std::cos(s);
 }
 
 int meas_dim(int kind) {
@@ -685,6 +703,22 @@ int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose7) {
   pose_set_pose_kernel<<<(unsigned)((h->B * 7 + 255) / 256), 256, 0, h->stream>>>(h->d_state, h->d_tmp, h->B);
   CK(cudaGetLastError());
   h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+
+int uwvkf_debug_eval(uwvkf_handle h, int what, const double *in, double *out, int n) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!in || !out || n <= 0 || what < 0 || what > UWVKF_DEBUG_WARP_SUM) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
+  int rc = ensure_tmp(h, (size_t)n * 12 * sizeof(double));
+  if (rc) return rc;
+  double *din = h->d_tmp, *dout = h->d_tmp + (size_t)n * 8;
+  CK(cudaMemcpyAsync(din, in, (size_t)n * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  debug_eval_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(what, din, dout, n, h->pp);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaMemcpyAsync(out, dout, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return UWVKF_OK;
 }
