@@ -71,13 +71,17 @@ enum uwvkf_pose_meas {
   UWVKF_POSE_VELOCITY = 4,       /* Velocity (DVL) m=3                           src/PoseUKF.cpp:476-482 */
   UWVKF_POSE_WATER_VELOCITY = 5, /* ADCP m=2, aux = cell_weighting, gate d2p95   src/PoseUKF.cpp:604-611 */
   UWVKF_POSE_GEOGRAPHIC = 6,     /* lat/lon [rad] m=2, aux = gps_in_body[3], d2p95 src/PoseUKF.cpp:567-579 */
-  UWVKF_POSE_DELAYED_XY = 7      /* m=2, aux = delayed_position[2]               src/PoseUKF.cpp:514-527 */
+  UWVKF_POSE_DELAYED_XY = 7,     /* m=2, aux = delayed_position[2]               src/PoseUKF.cpp:514-527 */
+  UWVKF_POSE_BODY_EFFORTS = 8,   /* BodyEffortsMeasurement m=6 (forces, torques), measurementEfforts: the Fossen model with the
+                                    inertia / damping blocks of the state                src/PoseUKF.cpp:153-196, 581-602 */
+  UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY = 9 /* same with only_affect_velocity = true: constrainVelocity, :198-219, 585-594 */
 };
 
 #define UWVKF_POSE_DIM 54
 #define UWVKF_POSE_DOF 53
 #define UWVKF_POSE_NPARAMS 22
 #define UWVKF_POSE_NOFFSETS 28
+#define UWVKF_UWV_NPARAMS 116
 
 /* flat PoseUKF::PoseUKFParameter (src/PoseUKF.hpp:46-76) preceded by the projection origin that the
  * reference keeps in its GeographicProjection member (src/PoseUKF.cpp:356,390) */
@@ -122,6 +126,10 @@ int uwvkf_clear_status(uwvkf_handle h);
 /* ---- PoseUKF -------------------------------------------------------------------------------------- */
 /* PoseUKFParameter + projection origin (src/PoseUKF.cpp:358-371, 356): params[UWVKF_POSE_NPARAMS], shared. */
 int uwvkf_pose_set_params(uwvkf_handle h, const double *params);
+/* model_parameters of the constructors (uwv_dynamic_model::UWVParameters -> dynamic_model, src/PoseUKF.cpp:353-354,382-383):
+ * flat UWVKF_UWV_NPARAMS doubles = inertia 6x6, linear damping 6x6, quadratic damping 6x6 (row-major), cog[3], cob[3], weight,
+ * buoyancy; shared by the batch.  Needed by the UWVKF_POSE_BODY_EFFORTS* updates only (else UWVKF_ERR_NOT_INITIALIZED). */
+int uwvkf_pose_set_model_parameters(uwvkf_handle h, const double *uwv_params);
 /* Markov offsets (inertia 9, lin_damping 9, quad_damping 9, water_density) per filter, host pointer;
  * overrides what uwvkf_set_state latched (src/PoseUKF.cpp:346-349). */
 int uwvkf_pose_set_offsets(uwvkf_handle h, const double *offsets, int64_t first, int64_t count);
@@ -159,7 +167,6 @@ enum uwvkf_velocity_meas {
 };
 /* flat uwv_dynamic_model::UWVParameters: inertia 6x6, linear damping 6x6, quadratic damping 6x6 (row-major),
  * distance_body2centerofgravity[3], distance_body2centerofbuoyancy[3], weight, buoyancy */
-#define UWVKF_UWV_NPARAMS 116
 /* setupMotionModel(parameters) (src/VelocityUKF.cpp:58-77); uwvkf_predict fails with UWVKF_ERR_NOT_INITIALIZED
  * ("Motion model is not initialized!", :117-118) until this was called. */
 int uwvkf_velocity_setup_motion_model(uwvkf_handle h, const double *uwv_params);

@@ -8,9 +8,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST, DEVICE = 0, 1
 FILTER_POSE, FILTER_VELOCITY, FILTER_BOTTOM, FILTER_INDIRECT_POSE = 0, 1, 2, 3
 (POSE_XY, POSE_Z, POSE_PRESSURE, POSE_ACCELERATION, POSE_VELOCITY, POSE_WATER_VELOCITY, POSE_GEOGRAPHIC,
- POSE_DELAYED_XY) = range(8)
+ POSE_DELAYED_XY, POSE_BODY_EFFORTS, POSE_BODY_EFFORTS_VELOCITY_ONLY) = range(10)
 POSE_MEAS_DIM = {POSE_XY: 2, POSE_Z: 1, POSE_PRESSURE: 1, POSE_ACCELERATION: 3, POSE_VELOCITY: 3, POSE_WATER_VELOCITY: 2,
-                 POSE_GEOGRAPHIC: 2, POSE_DELAYED_XY: 2}
+                 POSE_GEOGRAPHIC: 2, POSE_DELAYED_XY: 2, POSE_BODY_EFFORTS: 6, POSE_BODY_EFFORTS_VELOCITY_ONLY: 6}
 ST_NOT_SPD, ST_NAN_MEASUREMENT, ST_GATE_REJECTED, ST_MEAN_NOT_CONVERGED = 1, 2, 4, 8
 ERR_NAN_MEASUREMENT = -4
 
@@ -57,6 +57,7 @@ def load_library():
         lib.uwvkf_set_mean_policy.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.uwvkf_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         lib.uwvkf_pose_set_params.argtypes = [C.c_void_p, C.c_void_p]
+        lib.uwvkf_pose_set_model_parameters.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_pose_set_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         lib.uwvkf_pose_set_rotation_rate.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_pose_get_rotation_rate.argtypes = [C.c_void_p, C.c_void_p]
@@ -287,6 +288,12 @@ class PoseUKFBatch(_FilterBatch):
         p = _f64(params)
         assert p.shape == (22,)
         self._ck(self._lib.uwvkf_pose_set_params(self._h, _ptr(p)))
+
+    def set_model_parameters(self, uwv_params):
+        """model_parameters of the constructors (flat uwv_dynamic_model::UWVParameters, 116): needed by the body-efforts updates."""
+        p = _f64(uwv_params)
+        assert p.shape == (116,)
+        self._ck(self._lib.uwvkf_pose_set_model_parameters(self._h, _ptr(p)))
 
     def set_offsets(self, offsets, first=0):
         o = _f64(offsets)

@@ -39,7 +39,7 @@ struct uwvkf_filter_s {
   double *d_tmp = nullptr;
   size_t tmp_bytes = 0;
   // PoseUKF
-  double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr;
+  double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr, *d_uwv = nullptr;
   uwvkf::pose::Params pp{};
   bool have_params = false, have_Q = false;
   // small filters: state[B][dim + dof*dof], controls, shared process noise

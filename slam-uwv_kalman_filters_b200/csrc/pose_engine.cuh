@@ -33,7 +33,9 @@ enum { T_POS = 0, T_ORI = 3, T_VEL = 6, T_ACC = 9, T_BG = 12, T_BA = 15, T_G = 1
 enum { ST_NOT_SPD = 1u, ST_NAN_MEAS = 2u, ST_GATE_REJECTED = 4u, ST_MEAN_NOT_CONVERGED = 8u };
 
 enum MeasKind { M_XY = 0, M_Z = 1, M_PRESSURE = 2, M_ACCELERATION = 3, M_VELOCITY = 4, M_WATER_VELOCITY = 5,
-                M_GEOGRAPHIC = 6, M_DELAYED_XY = 7 };
+                M_GEOGRAPHIC = 6, M_DELAYED_XY = 7, M_BODY_EFFORTS = 8, M_BODY_EFFORTS_VELOCITY_ONLY = 9 };
+constexpr int MAXM = 6;      // largest measurement dimension (body efforts)
+constexpr int NUWV = 116;    // flat uwv_dynamic_model::UWVParameters: inertia, lin damping, quad damping (6x6 row-major), cog, cob, W, B
 
 struct Params {
   TMercConst tm;
@@ -53,7 +55,7 @@ struct Op {
   const double *z;     // device [B][m]
   const double *Rdev;  // device [B][m*m] or nullptr -> R below
   const uint8_t *valid;  // device [B] or nullptr
-  double R[9];
+  double R[MAXM * MAXM];
   double aux[4];
 };
 
@@ -63,6 +65,7 @@ struct Launch {
   const double *rot_rate;  // [B][3]
   uint32_t *status;        // [B]
   const double *Q;         // packed lower, column-major, NP doubles
+  const double *uwv;       // NUWV doubles (motion-model parameters of the constructor, src/PoseUKF.cpp:353-354) or nullptr
   long long B;
   int nops;
   Op ops[3];
@@ -78,7 +81,7 @@ __device__ __forceinline__ int sidx(int a, int b) { return a >= b ? cidx(a, b) :
 // per-warp shared-memory layout (doubles)
 template <int KMAX>
 struct WL {
-  static constexpr int MG = 3;                                      // rows of G / T / KS (max measurement dim)
+  static constexpr int MG = KMAX >= 48 ? MAXM : 3;                  // rows of G / T / KS (max measurement dim)
   static constexpr int LSZ = ((KMAX * (KMAX + 1) / 2 + 1) / 2) * 2;
   static constexpr int KE = ((KMAX + 1) / 2) * 2;
   static constexpr int L = BLK;             // leading-block Cholesky factor, packed by columns (dimension K)
@@ -464,19 +467,19 @@ __device__ __forceinline__ bool apply_delta(double *w, const Params &P, int lane
 template <int KIND> struct Meas;
 template <> struct Meas<M_XY> {   // src/PoseUKF.cpp:87-92
   static constexpr int K = 2, M = 2;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o, const double * = nullptr) {
     o[0] = mu[P_POS] + d(0); o[1] = mu[P_POS + 1] + d(1);
   }
 };
 template <> struct Meas<M_Z> {    // src/PoseUKF.cpp:100-105
   static constexpr int K = 3, M = 1;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o, const double * = nullptr) {
     o[0] = mu[P_POS + 2] + d(2);
   }
 };
 template <> struct Meas<M_VELOCITY> {   // src/PoseUKF.cpp:117-123
   static constexpr int K = 9, M = 3;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o, const double * = nullptr) {
     Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
     Vec3 v = qrot_inv(q, Vec3{mu[P_VEL] + d(6), mu[P_VEL + 1] + d(7), mu[P_VEL + 2] + d(8)});
     o[0] = v.x; o[1] = v.y; o[2] = v.z;
@@ -484,7 +487,7 @@ template <> struct Meas<M_VELOCITY> {   // src/PoseUKF.cpp:117-123
 };
 template <> struct Meas<M_ACCELERATION> {   // src/PoseUKF.cpp:125-131
   static constexpr int K = 19, M = 3;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *, const Params &, double *o, const double * = nullptr) {
     Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
     Vec3 a{mu[P_ACC] + d(9), mu[P_ACC + 1] + d(10), (mu[P_ACC + 2] + d(11)) + (mu[P_G] + d(18))};
     Vec3 v = qrot_inv(q, a);
@@ -493,7 +496,7 @@ template <> struct Meas<M_ACCELERATION> {   // src/PoseUKF.cpp:125-131
 };
 template <> struct Meas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115 ; aux = pressure_sensor_in_imu
   static constexpr int K = 53, M = 1;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o, const double * = nullptr) {
     Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
     Vec3 rn = qrot(q, Vec3{aux[0], aux[1], aux[2]});
     double zn = (mu[P_POS + 2] + d(2)) + rn.z;
@@ -502,7 +505,7 @@ template <> struct Meas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115 ; aux = press
 };
 template <> struct Meas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151 ; aux[0] = cell_weighting
   static constexpr int K = 52, M = 2;
-  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &, double *o) {
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &, double *o, const double * = nullptr) {
     Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
     double vx = mu[P_VEL] + d(6), vy = mu[P_VEL + 1] + d(7), vz = mu[P_VEL + 2] + d(8);
     Vec3 b = qrot_inv(q, Vec3{vx - (mu[P_WVB] + d(48)), vy - (mu[P_WVB + 1] + d(49)), vz - 0.0});
@@ -513,6 +516,100 @@ template <> struct Meas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151 ; aux[0
   }
 };
 
+
+// ---- uwv_dynamic_model::DynamicModel::calcEfforts with the inertia / damping blocks of a sigma point ----------------
+// tau = M nu_dot + C(M, nu) + D_lin nu + D_quad (|nu| o nu) + g(q)   (SURVEY.md Appendix D).
+// `base` = flat UWVParameters; blk(which, i, j) returns entry (i, j) of the state's 3x3 inertia (0) / linear (1) /
+// quadratic (2) damping block, which replaces rows / columns {0, 1, 5} of the 6x6 matrix (reference src/PoseUKF.cpp:160-171).
+template <bool SUBST, class Blk>
+__device__ __forceinline__ void calc_efforts_dev(const double *base, Blk blk, const double *acc6, const double *vel6, const Quat &q,
+                                                 double *out) {
+  auto el = [&](int which, int r, int c) {
+    const bool sr = (r < 2 || r == 5), sc = (c < 2 || c == 5);
+    if (SUBST && sr && sc) return blk(which, r == 5 ? 2 : r, c == 5 ? 2 : c);
+    return base[which * 36 + r * 6 + c];
+  };
+  double mv[6], ma[6], dl[6], dq[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double m = el(0, r, c);
+      s0 += m * vel6[c];
+      s1 += m * acc6[c];
+      s2 += el(1, r, c) * vel6[c];
+      s3 += el(2, r, c) * (fabs(vel6[c]) * vel6[c]);
+    }
+    mv[r] = s0; ma[r] = s1; dl[r] = s2; dq[r] = s3;
+  }
+  auto cross = [](const double *a, const double *b, double *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  double c0[3], c1[3], c2[3];
+  cross(mv, vel6 + 3, c0);
+  cross(mv, vel6, c1);
+  cross(mv + 3, vel6 + 3, c2);
+  const double W = base[114], Bu = base[115];
+  const Vec3 gf = qrot_inv(q, Vec3{0, 0, W - Bu});
+  const Vec3 gu = qrot_inv(q, Vec3{0, 0, 1});
+  const double lever[3] = {base[108] * W - base[111] * Bu, base[109] * W - base[112] * Bu, base[110] * W - base[113] * Bu};
+  const double guv[3] = {gu.x, gu.y, gu.z}, gfv[3] = {gf.x, gf.y, gf.z};
+  double gt[3];
+  cross(lever, guv, gt);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    out[i] = ma[i] + (c0[i] + dl[i] + dq[i] + gfv[i]);
+    out[3 + i] = ma[3 + i] + (c1[i] + c2[i] + dl[3 + i] + dq[3 + i] + gt[i]);
+  }
+}
+
+// per-filter context of the body-efforts models, evaluated at the MEAN before the update (reference src/PoseUKF.cpp:585-598):
+// ctx[0..2] = rotation_rate_body = getRotationRate(), [3..5] = w x imu_in_body, [6..8] = w x (w x imu_in_body),
+// velocity-only variant: [9..11] = q^-1 water_velocity, [12..14] = acceleration_body, [15..18] = q
+__device__ __forceinline__ void efforts_context(const double *mu, const double *wm, const Params &P, double *ctx) {
+  const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
+  const double lat = tmerc_nav_to_lat(P.tm, mu[P_POS], mu[P_POS + 1]);
+  const Vec3 eb = qrot_inv(q, Vec3{kEarthW * cos(lat), 0.0, kEarthW * sin(lat)});
+  const double w[3] = {wm[0] - mu[P_BG] - eb.x, wm[1] - mu[P_BG + 1] - eb.y, wm[2] - mu[P_BG + 2] - eb.z};
+  const double *r = P.imu_in_body;
+  const double c[3] = {w[1] * r[2] - w[2] * r[1], w[2] * r[0] - w[0] * r[2], w[0] * r[1] - w[1] * r[0]};
+  const double cc[3] = {w[1] * c[2] - w[2] * c[1], w[2] * c[0] - w[0] * c[2], w[0] * c[1] - w[1] * c[0]};
+  const Vec3 wvb = qrot_inv(q, Vec3{mu[P_WV], mu[P_WV + 1], 0.0});
+  const Vec3 ab = qrot_inv(q, Vec3{mu[P_ACC], mu[P_ACC + 1], mu[P_ACC + 2]});
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ctx[k] = w[k]; ctx[3 + k] = c[k]; ctx[6 + k] = cc[k]; }
+  ctx[9] = wvb.x; ctx[10] = wvb.y; ctx[11] = wvb.z;
+  ctx[12] = ab.x - cc[0]; ctx[13] = ab.y - cc[1]; ctx[14] = ab.z - cc[2];
+  ctx[15] = q.x; ctx[16] = q.y; ctx[17] = q.z; ctx[18] = q.w;
+}
+
+template <> struct Meas<M_BODY_EFFORTS> {   // measurementEfforts, src/PoseUKF.cpp:153-196; aux = ctx, model = UWVParameters
+  static constexpr int K = 48, M = 6;       // reads q, v, a, the 27 model states and the water velocity (tangent 3..47)
+  template <class D> __device__ static void eval(const double *mu, D d, const double *ctx, const Params &, double *o, const double *model) {
+    const Quat q = so3_boxplus(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Vec3{d(3), d(4), d(5)}, 1.0);
+    const Vec3 vb = qrot_inv(q, Vec3{mu[P_VEL] + d(6), mu[P_VEL + 1] + d(7), mu[P_VEL + 2] + d(8)});
+    const Vec3 wvb = qrot_inv(q, Vec3{mu[P_WV] + d(T_WV), mu[P_WV + 1] + d(T_WV + 1), 0.0});
+    const Vec3 ab = qrot_inv(q, Vec3{mu[P_ACC] + d(9), mu[P_ACC + 1] + d(10), mu[P_ACC + 2] + d(11)});
+    const double vel6[6] = {vb.x - ctx[3] - wvb.x, vb.y - ctx[4] - wvb.y, vb.z - ctx[5] - wvb.z, ctx[0], ctx[1], ctx[2]};
+    const double acc6[6] = {ab.x - ctx[6], ab.y - ctx[7], ab.z - ctx[8], 0.0, 0.0, 0.0};
+    // state blocks are MTK::matrix<3,3>, vectorised column-major (src/PoseState.hpp:37)
+    auto blk = [&](int which, int i, int j) { const int k = which * 9 + j * 3 + i; return mu[P_INERTIA + k] + d(T_INERTIA + k); };
+    calc_efforts_dev<true>(model, blk, acc6, vel6, q, o);
+  }
+};
+template <> struct Meas<M_BODY_EFFORTS_VELOCITY_ONLY> {   // constrainVelocity, src/PoseUKF.cpp:198-219: reads the velocity only
+  static constexpr int K = 9, M = 6;
+  template <class D> __device__ static void eval(const double *mu, D d, const double *ctx, const Params &, double *o, const double *model) {
+    const Quat q{ctx[15], ctx[16], ctx[17], ctx[18]};
+    const Vec3 vb = qrot_inv(q, Vec3{mu[P_VEL] + d(6), mu[P_VEL + 1] + d(7), mu[P_VEL + 2] + d(8)});
+    const double vel6[6] = {vb.x - ctx[3] - ctx[9], vb.y - ctx[4] - ctx[10], vb.z - ctx[5] - ctx[11], ctx[0], ctx[1], ctx[2]};
+    const double acc6[6] = {ctx[12], ctx[13], ctx[14], 0.0, 0.0, 0.0};
+    auto blk = [&](int, int, int) { return 0.0; };
+    calc_efforts_dev<false>(model, blk, acc6, vel6, q, o);
+  }
+};
+
 template <int M>
 __device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
   if constexpr (M == 1) {
@@ -520,6 +617,38 @@ __device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
   } else if constexpr (M == 2) {
     double id = 1.0 / (S[0] * S[3] - S[1] * S[2]);
     Si[0] = S[3] * id; Si[1] = -S[1] * id; Si[2] = -S[2] * id; Si[3] = S[0] * id;
+  } else if constexpr (M > 3) {
+    // Gauss-Jordan with partial pivoting (what Eigen's fixed-size inverse does above 4x4, as SURVEY.md Appendix B.2 describes)
+    double a[M * M];
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) { a[i] = S[i]; Si[i] = (i / M == i % M) ? 1.0 : 0.0; }
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      int p = c;
+#pragma unroll
+      for (int r = c + 1; r < M; ++r) if (fabs(a[r * M + c]) > fabs(a[p * M + c])) p = r;
+#pragma unroll
+      for (int r = c + 1; r < M; ++r) {
+        if (r == p) {
+#pragma unroll
+          for (int k = 0; k < M; ++k) {
+            double t = a[r * M + k]; a[r * M + k] = a[c * M + k]; a[c * M + k] = t;
+            t = Si[r * M + k]; Si[r * M + k] = Si[c * M + k]; Si[c * M + k] = t;
+          }
+        }
+      }
+      const double ip = 1.0 / a[c * M + c];
+#pragma unroll
+      for (int k = 0; k < M; ++k) { a[c * M + k] *= ip; Si[c * M + k] *= ip; }
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        if (r != c) {
+          const double f = a[r * M + c];
+#pragma unroll
+          for (int k = 0; k < M; ++k) { a[r * M + k] -= f * a[c * M + k]; Si[r * M + k] -= f * Si[c * M + k]; }
+        }
+      }
+    }
   } else {
     double c00 = S[4] * S[8] - S[5] * S[7], c01 = S[5] * S[6] - S[3] * S[8], c02 = S[3] * S[7] - S[4] * S[6];
     double id = 1.0 / (S[0] * c00 + S[1] * c01 + S[2] * c02);
@@ -533,7 +662,7 @@ __device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
 // gate95: the reference's d2p95 (src/PoseUKF.cpp:275-286), otherwise accept_any.
 template <int KIND, int KMAX>
 __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const double *z, const double *Rm, const double *aux,
-                                       bool gate95, const Params &P, int lane, unsigned &status) {
+                                       bool gate95, const Params &P, int lane, unsigned &status, const double *model = nullptr) {
   using W = WL<KMAX>;
   using MM = Meas<KIND>;
   constexpr int K = MM::K, M = MM::M;
@@ -552,7 +681,7 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
     const int j = (p - 1) >> 1;
     const double sg = (p & 1) ? 1.0 : -1.0;
     auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
-    MM::eval(mu, d, aux, P, Z[r]);
+    MM::eval(mu, d, aux, P, Z[r], model);
     wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
   }
   // mean (ukfom mean_sigma_points on a vector manifold)

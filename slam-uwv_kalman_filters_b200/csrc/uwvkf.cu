@@ -47,9 +47,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a
       }
       if (op.valid && !op.valid[f]) continue;
       const int kind = op.kind;
-      const int m = (kind == pose::M_Z || kind == pose::M_PRESSURE) ? 1 : ((kind == pose::M_VELOCITY || kind == pose::M_ACCELERATION) ? 3 : 2);
-      double z[3], R[9];
+      const bool efforts = (kind == pose::M_BODY_EFFORTS || kind == pose::M_BODY_EFFORTS_VELOCITY_ONLY);
+      const int m = efforts ? 6 : ((kind == pose::M_Z || kind == pose::M_PRESSURE) ? 1 : ((kind == pose::M_VELOCITY || kind == pose::M_ACCELERATION) ? 3 : 2));
+      constexpr int MZ = KMAX >= 48 ? pose::MAXM : 3;
+      double z[MZ], R[MZ * MZ];
       bool bad = false;
+      if (m > MZ) continue;   // six-dimensional measurements are routed to the dense instantiation by the host
       for (int k = 0; k < m; ++k) { z[k] = op.z[f * m + k]; bad |= isnan(z[k]); }
       for (int k = 0; k < m * m; ++k) { R[k] = op.Rdev ? op.Rdev[f * m * m + k] : op.R[k]; bad |= isnan(R[k]); }
       if (bad) { st |= pose::ST_NAN_MEAS; continue; }
@@ -75,6 +78,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a
           if constexpr (KMAX >= 53) {
             if (kind == pose::M_PRESSURE) dirty |= pose::update<pose::M_PRESSURE, KMAX>(w, lut, z, R, op.aux, false, P, lane, st);
             else if (kind == pose::M_WATER_VELOCITY) dirty |= pose::update<pose::M_WATER_VELOCITY, KMAX>(w, lut, z, R, op.aux, true, P, lane, st);
+            else if (efforts) {   // reference src/PoseUKF.cpp:581-602; the context is evaluated at the mean, once per filter
+              double *ctx = w + W::F;
+              pose::efforts_context(w, a.rot_rate + f * 3, P, ctx);
+              __syncwarp();
+              if (kind == pose::M_BODY_EFFORTS) dirty |= pose::update<pose::M_BODY_EFFORTS, KMAX>(w, lut, z, R, ctx, false, P, lane, st, a.uwv);
+              else dirty |= pose::update<pose::M_BODY_EFFORTS_VELOCITY_ONLY, KMAX>(w, lut, z, R, ctx, false, P, lane, st, a.uwv);
+            }
           }
           break;
       }
@@ -280,6 +290,7 @@ int meas_dim(int kind) {
     case UWVKF_POSE_XY: case UWVKF_POSE_WATER_VELOCITY: case UWVKF_POSE_GEOGRAPHIC: case UWVKF_POSE_DELAYED_XY: return 2;
     case UWVKF_POSE_Z: case UWVKF_POSE_PRESSURE: return 1;
     case UWVKF_POSE_ACCELERATION: case UWVKF_POSE_VELOCITY: return 3;
+    case UWVKF_POSE_BODY_EFFORTS: case UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY: return 6;
   }
   return -1;
 }
@@ -343,18 +354,23 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
   pose::Launch L{};
   L.state = h->d_state; L.offsets = h->d_offsets; L.rot_rate = h->d_rot; L.status = h->d_status; L.Q = h->d_Q;
+  L.uwv = h->d_uwv;
   L.B = h->B; L.nops = nops;
-  bool slow = false;
+  bool slow = false, dense_only = false;
   for (int o = 0; o < nops; ++o) {
     L.ops[o] = ops[o];
     if (ops[o].type == 0 && !h->have_Q) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_set_process_noise was not called");
     if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_PRESSURE || ops[o].kind == UWVKF_POSE_WATER_VELOCITY)) slow = true;
+    if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_BODY_EFFORTS || ops[o].kind == UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY)) {
+      if (!h->d_uwv) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_model_parameters was not called");
+      slow = dense_only = true;
+    }
   }
   // engine selection: "panel + stream" kernel for predict / update / predict+update (pressure and ADCP through their
   // affine tail); the resident kernel (dense prefix 53 for pressure / ADCP) for op sequences the fused kernel has no
   // instantiation for and, with UWVKF_ENGINE=v1, for everything (cross-checks)
   static const bool force_v1 = [] { const char *e = std::getenv("UWVKF_ENGINE"); return e && std::string(e) == "v1"; }();
-  if (!force_v1) {
+  if (!force_v1 && !dense_only) {
     if (nops == 1 && ops[0].type == 0) return launch_fused<1, pose::M_NONE>(h, L);
     if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
     if (nops == 2 && ops[0].type == 0 && ops[1].type == 1) return launch_fused_kind<1>(h, L, ops[1].kind);
@@ -393,10 +409,11 @@ int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, i
     if (nr <= 1024 * 9) for (int64_t k = 0; k < nr; ++k) if (std::isnan(R[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement covariance contains NaN");
   }
   const void *p;
-  int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * 3 * sizeof(double), memspace, (void **)&h->d_z, &p);
+  int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * pose::MAXM * sizeof(double), memspace, (void **)&h->d_z, &p);
   if (rc) return rc;
   op.z = (const double *)p;
   if (R_per_filter) {
+    if (m > 3) return fail(UWVKF_ERR_UNSUPPORTED, "per-filter R is supported for measurement dimensions <= 3");
     rc = stage(h, R, (size_t)h->B * m * m * sizeof(double), (size_t)h->B * 9 * sizeof(double), memspace, (void **)&h->d_Rpf, &p);
     if (rc) return rc;
     op.Rdev = (const double *)p;
@@ -470,7 +487,7 @@ int uwvkf_destroy(uwvkf_handle h) {
   if (!h) return UWVKF_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
-  cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp);
+  cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp); cudaFree(h->d_uwv);
   small_destroy(h);
   delete h;
   return UWVKF_OK;
@@ -604,6 +621,16 @@ int uwvkf_pose_set_params(uwvkf_handle h, const double *p) {
   P.wv_scale = p[UWVKF_PP_WV_SCALE]; P.adcp_bias_tau = p[UWVKF_PP_ADCP_BIAS_TAU];
   P.atm_pressure = p[UWVKF_PP_ATM_PRESSURE]; P.rho_tau = p[UWVKF_PP_WATER_DENSITY_TAU];
   h->have_params = true;
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_set_model_parameters(uwvkf_handle h, const double *uwv) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!uwv) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null model parameters");
+  for (int k = 0; k < pose::NUWV; ++k) if (std::isnan(uwv[k])) return fail(UWVKF_ERR_INVALID_ARGUMENT, "model parameters contain NaN");
+  if (!h->d_uwv) CK(cudaMalloc(&h->d_uwv, pose::NUWV * sizeof(double)));
+  CK(cudaMemcpyAsync(h->d_uwv, uwv, pose::NUWV * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return UWVKF_OK;
 }
 

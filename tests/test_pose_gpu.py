@@ -191,6 +191,49 @@ def test_fused_predict_update_parity(pkg, syn, scen, kind):
     ukf.close()
 
 
+@pytest.mark.parametrize("velocity_only", [False, True])
+def test_body_efforts_update_parity(pkg, syn, scen, velocity_only):
+    """integrateMeasurement(BodyEffortsMeasurement, only_affect_velocity) (reference src/PoseUKF.cpp:581-602): the Fossen model
+    with the inertia / damping blocks of each sigma point (m = 6, tangent prefix 48), or constrainVelocity (prefix 9)."""
+    B = 12
+    par = scen["par"].copy()
+    par[19:22] = [0.2, -0.1, 0.05]   # imu_in_body lever arm
+    filt = np.arange(B)
+    mu, cov = syn.pose_initial_batch(filt, scen["cfg"])
+    ukf = pkg.PoseUKFBatch(B, par)
+    ukf.set_process_noise(scen["Q"])
+    ukf.set_state(mu, cov)
+    off = np.concatenate([mu[:, 20:47], mu[:, 53:54]], axis=1)
+    uwv = syn.uwv_params_flat()
+    uwv[108:114] = [0.0, 0.0, 0.02, 0.0, 0.0, -0.01]   # cog / cob levers so that the restoring torque is exercised
+    uwv[115] = 1490.0
+    with pytest.raises(pkg.UwvkfError) as ei:             # model parameters are required first
+        ukf.integrate_measurement(pkg.POSE_BODY_EFFORTS, np.zeros((B, 6)), np.eye(6))
+    assert ei.value.code == -5
+    ukf.set_model_parameters(uwv)
+    for s in range(1, 4):   # a few steps so that Sigma is dense
+        inp = syn.pose_inputs(filt, s)
+        ukf.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    mu, cov = ukf.get_state()
+    inp = syn.pose_inputs(filt, 4)
+    w = inp["gyro"]
+    ukf.integrate_rotation_rate(w)
+    z = np.ascontiguousarray(syn.velocity_inputs(filt, 4)["efforts"])
+    R = np.diag([4.0, 4.0, 4.0, 0.25, 0.25, 0.25])
+    kind = pkg.POSE_BODY_EFFORTS_VELOCITY_ONLY if velocity_only else pkg.POSE_BODY_EFFORTS
+    okind = orc.BODY_EFFORTS_VEL if velocity_only else orc.BODY_EFFORTS
+    ukf.integrate_measurement(kind, z, R)
+    gmu, gcov = ukf.get_state()
+    omu, ocov = mu.copy(), cov.copy()
+    for f in range(B):
+        omu[f], ocov[f], st, _ = orc.pose_update(okind, mu[f], cov[f], z[f], R, uwv, w[f], par)
+        assert st == 0
+    assert not ukf.get_status().any()
+    assert np.abs(gmu - mu).max() > 1e-6, "the update must move the state"
+    assert_parity(gmu, gcov, omu, ocov, f"body efforts (velocity_only={velocity_only})")
+    ukf.close()
+
+
 def test_lockstep_sequence_parity(pkg, syn, scen):
     """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
     step so that the asserted error is the per-step error of north_star."""
