@@ -181,6 +181,8 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
   UWVKF_MEASUREMENT(Acceleration, 3)
   UWVKF_MEASUREMENT(Velocity, 3)
   UWVKF_MEASUREMENT(WaterVelocityMeasurement, 2)
+  UWVKF_MEASUREMENT(BodyEffortsMeasurement, 6)
+  UWVKF_MEASUREMENT(VisualFeatureMeasurement, 2)
 
   // reference src/PoseUKF.cpp:288-372: state and covariance derived from the configuration
   PoseUKF(const Vector3d &imu_in_nwu_pos, const Matrix3d &imu_in_nwu_pos_cov, const Quaterniond &imu_in_nwu_rot,
@@ -238,13 +240,15 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
     fp.adcp_bias_tau = cfg.water_velocity.adcp_bias_tau; fp.atmospheric_pressure = cfg.hydrostatics.atmospheric_pressure;
     fp.water_density_tau = cfg.hydrostatics.water_density_tau;
     setParameters(cfg.location, fp);
+    setModelParameters(model_parameters);   // dynamic_model.reset(new DynamicModel()); setUWVParameters(...)  :353-354
     initializeFilter(s, P);
   }
   // reference src/PoseUKF.cpp:374-391: full state + covariance + persistent parameters
   PoseUKF(const State &initial_state, const Covariance &state_cov, const LocationConfiguration &location,
-          const UWVParameters & /*model_parameters*/, const PoseUKFParameter &filter_parameter, int64_t batch = 1, int device = 0)
+          const UWVParameters &model_parameters, const PoseUKFParameter &filter_parameter, int64_t batch = 1, int device = 0)
       : FilterBase(UWVKF_FILTER_POSE, batch, device) {
     setParameters(location, filter_parameter);
+    setModelParameters(model_parameters);   // :382-383
     initializeFilter(initial_state, state_cov);
   }
 
@@ -306,6 +310,32 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
   }
   void integrateMeasurement(const Acceleration &m) { update(UWVKF_POSE_ACCELERATION, m.mu.data(), m.cov.data(), nullptr); }
   void integrateMeasurement(const Velocity &m) { update(UWVKF_POSE_VELOCITY, m.mu.data(), m.cov.data(), nullptr); }
+  // reference src/PoseUKF.cpp:581-602 (forces and torques in the body frame; m = 6)
+  void integrateMeasurement(const BodyEffortsMeasurement &m, bool only_affect_velocity = false) {
+    update(only_affect_velocity ? UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY : UWVKF_POSE_BODY_EFFORTS, m.mu.data(), m.cov.data(), nullptr);
+  }
+  // reference src/PoseUKF.cpp:613-654 (features of a visual marker in undistorted image coordinates)
+  void integrateMeasurement(const std::vector<VisualFeatureMeasurement> &marker_features, const std::vector<Vector3d> &feature_positions,
+                            const Affine3d &marker_pose, const Matrix6d &cov_marker_pose, const CameraConfiguration &camera_config,
+                            const Affine3d &camera_in_IMU) {
+    // the reference loops with `||` over both vectors (src/PoseUKF.cpp:633): unequal sizes read out of bounds there
+    if (marker_features.size() != feature_positions.size()) throw std::runtime_error("uwvkf: marker_features and feature_positions must have equal size");
+    const int n = (int)marker_features.size();
+    std::vector<double> px((size_t)batch_ * n * 2), pc((size_t)n * 4), fp((size_t)n * 3);
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(&pc[i * 4], marker_features[i].cov.data(), 4 * sizeof(double));
+      std::memcpy(&fp[i * 3], feature_positions[i].data(), 3 * sizeof(double));
+      for (int64_t f = 0; f < batch_; ++f) std::memcpy(&px[(f * n + i) * 2], marker_features[i].mu.data(), 2 * sizeof(double));
+    }
+    auto pack = [](const Affine3d &a, double *p) {
+      p[0] = a.translation[0]; p[1] = a.translation[1]; p[2] = a.translation[2];
+      p[3] = a.rotation.x; p[4] = a.rotation.y; p[5] = a.rotation.z; p[6] = a.rotation.w;
+    };
+    double mp[7], ci[7], cam[4] = {camera_config.fx, camera_config.fy, camera_config.cx, camera_config.cy};
+    pack(marker_pose, mp);
+    pack(camera_in_IMU, ci);
+    detail::check(uwvkf_pose_update_features(h_, n, px.data(), pc.data(), fp.data(), mp, cov_marker_pose.data(), cam, ci, nullptr, UWVKF_HOST));
+  }
   void integrateMeasurement(const WaterVelocityMeasurement &m, double cell_weighting) {
     update(UWVKF_POSE_WATER_VELOCITY, m.mu.data(), m.cov.data(), &cell_weighting);
   }
@@ -332,6 +362,9 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
   }
 
  private:
+  void setModelParameters(const UWVParameters &model_parameters) {
+    detail::check(uwvkf_pose_set_model_parameters(h_, model_parameters.flat().data()));
+  }
   void setParameters(const LocationConfiguration &loc, const PoseUKFParameter &fp) {
     double p[UWVKF_POSE_NPARAMS] = {0};
     p[UWVKF_PP_LAT0] = loc.latitude; p[UWVKF_PP_LON0] = loc.longitude;
@@ -354,7 +387,8 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
     return t;
   }
   void update(int kind, const double *z, const double *R, const double *aux) {
-    const int m = (kind == UWVKF_POSE_Z || kind == UWVKF_POSE_PRESSURE) ? 1 : ((kind == UWVKF_POSE_VELOCITY || kind == UWVKF_POSE_ACCELERATION) ? 3 : 2);
+    const int m = (kind == UWVKF_POSE_BODY_EFFORTS || kind == UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY) ? 6 :
+                  (kind == UWVKF_POSE_Z || kind == UWVKF_POSE_PRESSURE) ? 1 : ((kind == UWVKF_POSE_VELOCITY || kind == UWVKF_POSE_ACCELERATION) ? 3 : 2);
     detail::check(uwvkf_pose_update(h_, kind, tile(z, m).data(), R, 0, aux, nullptr, UWVKF_HOST));
   }
 };

@@ -153,6 +153,14 @@ int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const doub
 int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int meas_kind, const double *z,
                               const double *R, int R_per_filter, const double *aux, const uint8_t *valid,
                               int memspace);
+/* integrateMeasurement(marker_features, feature_positions, marker_pose, cov_marker_pose, camera_config, camera_in_IMU)
+ * (src/PoseUKF.cpp:613-654): the state is augmented with the marker pose (59 DOF, 119 sigma points), one S2 update per
+ * feature, the leading 53 x 53 block is kept.  px[B][nfeat][2] pixel coordinates (memspace), pxcov[nfeat][4],
+ * feature_pos[nfeat][3] (marker frame), marker_pose[7] = t(3) q(x,y,z,w) in the navigation frame, cov_marker[36],
+ * camera = fx, fy, cx, cy, cam_in_imu[7]; 1 <= nfeat <= 8; valid[B] may be NULL. */
+int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, const double *pxcov, const double *feature_pos,
+                               const double *marker_pose, const double *cov_marker, const double *camera, const double *cam_in_imu,
+                               const uint8_t *valid, int memspace);
 /* Navigation solution of filters [first, first+count): out[count][10] = p(3) q(x,y,z,w) v(3) -- the leading
  * part of getCurrentState() that a caller reads every step.  Asynchronous for memspace == UWVKF_DEVICE. */
 int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace);

@@ -193,6 +193,26 @@ void meas_constrain_velocity(const double *s, double *z, const UwvParams &P, con
   calc_efforts(P, acc6, vel6, q, z);
 }
 
+// PoseStateWithMarker (src/PoseUKF.cpp:225-228): filter_state (53 DOF), marker_position, marker_orientation -> 59 DOF, 61 stored
+Layout pose_marker_layout() {
+  Layout l = pose_layout();
+  l.comps.push_back({VECT, 3, 3});
+  l.comps.push_back({SO3, 3, 4});
+  return l;
+}
+// src/PoseUKF.cpp:233-243  measurementVisualLandmark: the feature seen from the camera, as a point on S2.
+// cam_in_imu = (t[3], q[4]); nav_in_cam = (imu_in_nav * cam_in_imu)^-1
+void pose_landmark(const double *s /*61*/, double *z /*3*/, const double *feature_pos, const double *cam_in_imu) {
+  double cam_t[3], cam_q[4], fp[3], d[3];
+  quat_rot(s + P_ORI, cam_in_imu, cam_t);                       // imu_in_nav * cam_in_imu
+  for (int k = 0; k < 3; ++k) cam_t[k] += s[P_POS + k];
+  quat_mul(s + P_ORI, cam_in_imu + 3, cam_q);
+  quat_rot(s + P_DIM + 3, feature_pos, fp);                     // marker_orientation * feature_pos + marker_position
+  for (int k = 0; k < 3; ++k) d[k] = fp[k] + s[P_DIM + k] - cam_t[k];
+  quat_rot_inv(cam_q, d, z);
+  s2_normalize(z);                                               // MTK::S2<double>(vec) normalises
+}
+
 bool gate_any(double) { return true; }                 // ukfom::accept_any_mahalanobis_distance
 bool gate_d2p95(double d2) { return !(d2 > 5.991); }   // src/PoseUKF.cpp:275-286
 
@@ -309,6 +329,39 @@ int orc_pose_meas_dim(int kind) {
     case ORC_POSE_BODY_EFFORTS: case ORC_POSE_BODY_EFFORTS_VELOCITY_ONLY: return 6;
   }
   return -1;
+}
+
+// src/PoseUKF.cpp:613-654  integrateMeasurement(marker_corners, feature_positions, marker_pose, cov_marker_pose, camera_config,
+// camera_in_IMU): augment with the marker pose, one S2 update per feature, keep the leading 53 x 53 block.
+// px[nfeat][2], pxcov[nfeat][4], feature_pos[nfeat][3], marker_pose = t[3] q[4], cov_marker[36], camera = fx fy cx cy, cam_in_imu = t q
+int orc_pose_update_features(double *mu, double *cov, int nfeat, const double *px, const double *pxcov, const double *feature_pos,
+                             const double *marker_pose, const double *cov_marker, const double *camera, const double *cam_in_imu,
+                             const double *policy) {
+  const int NA = P_DOF + 6;
+  std::vector<double> amu(P_DIM + 7), acov((size_t)NA * NA, 0.0);
+  std::memcpy(amu.data(), mu, P_DIM * sizeof(double));                                  // :619-622
+  std::memcpy(amu.data() + P_DIM, marker_pose, 7 * sizeof(double));
+  for (int i = 0; i < P_DOF; ++i) for (int j = 0; j < P_DOF; ++j) acov[(size_t)i * NA + j] = cov[i * P_DOF + j];   // :623-625
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) acov[(size_t)(P_DOF + i) * NA + P_DOF + j] = cov_marker[i * 6 + j];
+  Ukf ukf(pose_marker_layout(), amu.data(), acov.data(), make_policy(policy));
+  const double fx = camera[0], fy = camera[1], cx = camera[2], cy = camera[3];
+  const double fx2 = std::pow(fx, 2.), fy2 = std::pow(fy, 2.), fxy = fx * fy;           // :628-630
+  Layout s2l{{{S2, 2, 3}}};
+  int status = 0;
+  for (int i = 0; i < nfeat; ++i) {                                                     // :633
+    if (has_nan(px + 2 * i, 2) || has_nan(pxcov + 4 * i, 4)) return ST_NAN_MEAS;        // :635
+    double z[3] = {(px[2 * i] - cx) / fx, (px[2 * i + 1] - cy) / fy, 1.0};              // :638-640
+    s2_normalize(z);
+    double R[4] = {pxcov[4 * i] / fx2, pxcov[4 * i + 1] / fxy, pxcov[4 * i + 2] / fxy, pxcov[4 * i + 3] / fy2};   // :642-644
+    const double *fp = feature_pos + 3 * i;
+    ukf.update(s2l, z, [&](const double *x, double *o) { pose_landmark(x, o, fp, cam_in_imu); }, R, gate_any);     // :646
+    status |= (int)ukf.status();
+  }
+  if (!(status & ST_NOT_SPD)) {                                                         // :653
+    std::memcpy(mu, ukf.mu().data(), P_DIM * sizeof(double));
+    for (int i = 0; i < P_DOF; ++i) for (int j = 0; j < P_DOF; ++j) cov[i * P_DOF + j] = ukf.sigma()[(size_t)i * NA + j];
+  }
+  return status;
 }
 
 int orc_pose_predict(double *mu, double *cov, const double *Q, const double *rot_rate, const double *params,

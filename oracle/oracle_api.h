@@ -51,6 +51,10 @@ int orc_pose_predict(double *mu, double *cov, const double *Q, const double *rot
                      const double *offsets28, double dt, const double *policy, int *mean_it);
 int orc_pose_update(int kind, double *mu, double *cov, const double *z, const double *R, const double *aux,
                     const double *rot_rate, const double *params, const double *policy, double *d2_out);
+/* visual-marker update on the marker-augmented state (src/PoseUKF.cpp:613-654); poses = t[3], q(x,y,z,w) */
+int orc_pose_update_features(double *mu, double *cov, int nfeat, const double *px, const double *pxcov, const double *feature_pos,
+                             const double *marker_pose, const double *cov_marker, const double *camera, const double *cam_in_imu,
+                             const double *policy);
 void orc_pose_rotation_rate(const double *mu, const double *rot_rate, const double *params, double *out);
 void orc_pose_init_from_config(const double *pos, const double *pos_cov, const double *quat, const double *rot_cov,
                                const double *cfg, const double *inertia6, const double *lin6, const double *quad6,

@@ -65,6 +65,7 @@ def load_library():
         lib.uwvkf_pose_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_pose_predict_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_pose_update_features.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int]
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -329,6 +330,14 @@ class PoseUKFBatch(_FilterBatch):
         if valid is not None and not isinstance(valid, int):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_update(self._h, kind, _ptr(z), _ptr(R), per, _ptr(aux), _ptr(valid), memspace))
+
+    def integrate_features(self, px, pxcov, feature_pos, marker_pose, cov_marker, camera, cam_in_imu, valid=None, memspace=HOST):
+        """integrateMeasurement(marker_features, feature_positions, marker_pose, cov_marker_pose, camera_config, camera_in_IMU)
+        (src/PoseUKF.cpp:613-654); px: [B, nfeat, 2] pixel coordinates, poses as t(3), q(x,y,z,w)."""
+        nfeat = np.asarray(feature_pos).shape[0]
+        self._ck(self._lib.uwvkf_pose_update_features(self._h, nfeat, _ptr(_f64(px)), _ptr(_f64(pxcov)), _ptr(_f64(feature_pos)),
+                                                      _ptr(_f64(marker_pose)), _ptr(_f64(cov_marker)), _ptr(_f64(camera)),
+                                                      _ptr(_f64(cam_in_imu)), _ptr(_u8(valid)), memspace))
 
     def predict_update(self, dt, w, kind, z, R, aux=None, valid=None, memspace=HOST):
         """Fused predictionStep(dt) + integrateMeasurement(kind) in one kernel (one HBM round trip)."""

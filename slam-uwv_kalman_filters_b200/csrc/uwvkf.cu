@@ -1,6 +1,7 @@
 // uwvkf C ABI (include/uwvkf.h) + kernel launchers.  Thin host code over the CUDA kernels; no CPU path.
 #include "internal.h"
 #include "pose_fused.cuh"
+#include "pose_marker.cuh"
 #include <cstdlib>
 
 namespace uwvkf {
@@ -700,6 +701,48 @@ int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int me
   int rc = make_update_op(h, meas_kind, z, R, R_per_filter, aux, valid, memspace, ops[1]);
   if (rc) return rc;
   return run_pose(h, 2, ops);
+}
+
+int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, const double *pxcov, const double *feature_pos,
+                               const double *marker_pose, const double *cov_marker, const double *camera, const double *cam_in_imu,
+                               const uint8_t *valid, int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (nfeat < 1 || nfeat > pose::MAXFEAT) return fail(UWVKF_ERR_INVALID_ARGUMENT, "1 <= nfeat <= 8");
+  if (!px || !pxcov || !feature_pos || !marker_pose || !cov_marker || !camera || !cam_in_imu) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
+  pose::MarkerArgs M{};
+  M.nfeat = nfeat;
+  for (int k = 0; k < nfeat * 4; ++k) M.pxcov[k / 4][k % 4] = pxcov[k];
+  for (int k = 0; k < nfeat * 3; ++k) M.feat[k / 3][k % 3] = feature_pos[k];
+  for (int k = 0; k < 7; ++k) { M.marker_pose[k] = marker_pose[k]; M.cam_in_imu[k] = cam_in_imu[k]; }
+  for (int k = 0; k < 36; ++k) M.cov_marker[k] = cov_marker[k];
+  for (int k = 0; k < 4; ++k) M.camera[k] = camera[k];
+  if (memspace == UWVKF_HOST && h->B <= 1024)   // checkMeasurment() throwing (src/PoseUKF.cpp:635); larger batches: per-filter status bit
+    for (int64_t k = 0; k < h->B * nfeat * 2; ++k) if (std::isnan(px[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "marker corner contains NaN");
+  for (int k = 0; k < nfeat * 4; ++k) if (std::isnan(pxcov[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "marker corner covariance contains NaN");
+  const double *dpx = px;
+  if (memspace == UWVKF_HOST) {
+    const size_t bytes = (size_t)h->B * nfeat * 2 * sizeof(double);
+    int rc = ensure_tmp(h, bytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_tmp, px, bytes, cudaMemcpyHostToDevice, h->stream));
+    dpx = h->d_tmp;
+  }
+  const void *pv;
+  int rc = stage(h, valid, (size_t)h->B, (size_t)h->B, memspace, (void **)&h->d_valid, &pv);
+  if (rc) return rc;
+  constexpr int WARPS = 6;
+  const size_t smem = (size_t)WARPS * pose::MarkerLayout::TOTAL * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(pose::pose_marker_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>((h->B + WARPS - 1) / WARPS, h->sm_count);
+  pose::pose_marker_kernel<WARPS><<<grid, WARPS * 32, smem, h->stream>>>(h->d_state, h->d_status, dpx, (const uint8_t *)pv, h->B, M, h->pp);
+  CK(cudaGetLastError());
+  h->launches++;
+  return UWVKF_OK;
 }
 
 int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace) {

@@ -64,6 +64,13 @@ int main() {
     pose.integrateMeasurement(a);
     if ((s + 1) % 5 == 0) pose.integrateMeasurement(p, Vector3d{0.3, -0.1, 0.2});
   }
+  {   // model-aided part: forces / torques in the body frame, both flavours (reference src/PoseUKF.cpp:581-602)
+    PoseUKF::BodyEffortsMeasurement e;
+    const double tau[6] = {12.0, -3.0, 1.5, 0.0, 0.0, 0.4};
+    for (int k = 0; k < 6; ++k) { e.mu[k] = tau[k]; e.cov(k, k) = k < 3 ? 4.0 : 0.25; }
+    pose.integrateMeasurement(e);
+    pose.integrateMeasurement(e, true);
+  }
   PoseUKF::State st; PoseUKF::Covariance cv;
   pose.getCurrentStateAndCovariance(st, cv);
   dump("POSE", st, 54, cv.v, 53 * 53);

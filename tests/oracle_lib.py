@@ -69,6 +69,15 @@ def pose_update(kind, mu, cov, z, R, aux, rot_rate, params, policy=None):
     return mu, cov, st, d2.value
 
 
+def pose_update_features(mu, cov, px, pxcov, feature_pos, marker_pose, cov_marker, camera, cam_in_imu, policy=None):
+    """PoseUKF::integrateMeasurement(marker_corners, ...) on the marker-augmented state. Returns (mu', cov', status)."""
+    mu, cov = _c(mu).copy(), _c(cov).copy()
+    px, fp = _c(px), _c(feature_pos)
+    st = lib().orc_pose_update_features(_p(mu), _p(cov), C.c_int(fp.shape[0]), _p(px), _p(_c(pxcov)), _p(fp), _p(_c(marker_pose)),
+                                        _p(_c(cov_marker)), _p(_c(camera)), _p(_c(cam_in_imu)), _p(_c(policy)))
+    return mu, cov, st
+
+
 def pose_rotation_rate(mu, rot_rate, params):
     out = np.zeros(3)
     lib().orc_pose_rotation_rate(_p(_c(mu)), _p(_c(rot_rate)), _p(_c(params)), _p(out))

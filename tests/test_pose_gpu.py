@@ -234,6 +234,56 @@ def test_body_efforts_update_parity(pkg, syn, scen, velocity_only):
     ukf.close()
 
 
+def _project_marker(mu, syn, marker_pose, features, cam_in_imu, camera):
+    """pixel coordinates of the marker features seen from the filter's mean pose (numpy restatement of the camera model)."""
+    import structured_ref as sr
+    cam_t = mu[0:3] + sr.qrot(mu[3:7], cam_in_imu[0:3])
+    cam_q = sr.qmul(mu[3:7], cam_in_imu[3:7])
+    px = np.zeros((features.shape[0], 2))
+    for k, ft in enumerate(features):
+        pc = sr.qrot(sr.qconj(cam_q), marker_pose[0:3] + sr.qrot(marker_pose[3:7], ft) - cam_t)
+        px[k] = [camera[0] * pc[0] / pc[2] + camera[2], camera[1] * pc[1] / pc[2] + camera[3]]
+    return px
+
+
+def test_visual_marker_update_parity(pkg, syn, scen):
+    """integrateMeasurement(marker_features, ...) on the 59-DOF marker-augmented state (reference src/PoseUKF.cpp:613-654):
+    119 sigma points, S2 innovation, one sequential update per corner, leading 53 x 53 block kept."""
+    import structured_ref as sr
+    B = 8
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    rng = np.random.default_rng(3)
+    # a marker 4 m ahead of the vehicle (seen from the mean pose of filter 0), slightly rotated, uncertain pose
+    mq = sr.so3_exp(np.array([0.05, -0.1, 0.2]))
+    marker_pose = np.concatenate([mu[0, 0:3] + sr.qrot(mu[0, 3:7], np.array([4.0, 0.3, -0.2])), sr.qmul(mu[0, 3:7], mq)])
+    covm = np.diag([4e-4, 4e-4, 9e-4, 1e-4, 1e-4, 4e-4])
+    covm[0, 1] = covm[1, 0] = 1e-4
+    pxcov = np.tile(np.array([0.25, 0.05, 0.05, 0.36]), (4, 1))
+    px = np.stack([_project_marker(mu[f], syn, marker_pose, syn.MARKER_FEATURES, syn.CAM_IN_BODY, syn.CAMERA) for f in range(B)])
+    px += 0.7 * rng.normal(size=px.shape)
+    valid = np.ones(B, dtype=np.uint8)
+    valid[5] = 0
+    ukf.integrate_features(px, pxcov, syn.MARKER_FEATURES, marker_pose, covm, syn.CAMERA, syn.CAM_IN_BODY, valid=valid)
+    gmu, gcov = ukf.get_state()
+    omu, ocov = mu.copy(), cov.copy()
+    for f in range(B):
+        if valid[f]:
+            omu[f], ocov[f], st = orc.pose_update_features(mu[f], cov[f], px[f], pxcov, syn.MARKER_FEATURES, marker_pose, covm,
+                                                           syn.CAMERA, syn.CAM_IN_BODY)
+            assert st == 0
+    assert not ukf.get_status().any()
+    assert np.array_equal(gmu[5], mu[5]) and np.array_equal(gcov[5], cov[5])
+    assert np.abs(gmu[0] - mu[0]).max() > 1e-6, "the update must move the state"
+    assert_parity(gmu, gcov, omu, ocov, "visual marker update (4 corners)")
+    # a NaN corner refuses the whole measurement for that filter (checkMeasurment()); small host batches raise like the reference
+    bad = px.copy(); bad[2, 1, 0] = np.nan
+    with pytest.raises(pkg.UwvkfError) as ei:
+        ukf.integrate_features(bad, pxcov, syn.MARKER_FEATURES, marker_pose, covm, syn.CAMERA, syn.CAM_IN_BODY)
+    assert ei.value.code == -4
+    ukf.close()
+
+
 def test_lockstep_sequence_parity(pkg, syn, scen):
     """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
     step so that the asserted error is the per-step error of north_star."""
