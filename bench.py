@@ -191,18 +191,47 @@ def main():
         g, z = dev_in[i % NR]
         ukf.predict_update(DT, g.data_ptr(), pkg.POSE_VELOCITY, z.data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
 
+    # end-to-end arm: every step uploads that step's gyro + DVL samples from pinned host memory, runs the fused step and
+    # reads the navigation solution (p, q, v) of every filter back to pinned host memory.  The three legs run on three
+    # streams with event dependencies (H2D of step i+1 and D2H of step i-1 overlap the kernel of step i), which is how a
+    # caller streams sensor data through the C ABI: the ABI takes device pointers and is asynchronous on the handle's stream.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    e2e_in = [(torch.empty((B, 3), dtype=torch.float64, device=dev), torch.empty((B, 3), dtype=torch.float64, device=dev)) for _ in range(2)]
+    e2e_nav = [torch.empty((B, 10), dtype=torch.float64, device=dev) for _ in range(2)]
+    e2e_host = [torch.empty((B, 10), dtype=torch.float64).pin_memory() for _ in range(2)]
+    ev_in, ev_main, ev_out = {}, {}, {}
+
     def step_e2e(i):
-        g, z = host_in[i % NR]
-        ukf.predict_update(DT, g.numpy(), pkg.POSE_VELOCITY, z.numpy(), syn.R_DVL, memspace=pkg.HOST)
-        ukf.get_navigation_into(nav_dev.data_ptr(), memspace=pkg.DEVICE)
+        slot = i % 2
+        with torch.cuda.stream(s_in):
+            if i - 2 in ev_main:
+                s_in.wait_event(ev_main[i - 2])          # the kernel that last read this input slot has finished
+            g, z = host_in[i % NR]
+            e2e_in[slot][0].copy_(g, non_blocking=True)
+            e2e_in[slot][1].copy_(z, non_blocking=True)
+            ev_in[i] = torch.cuda.Event()
+            ev_in[i].record(s_in)
         with torch.cuda.stream(stream):
-            nav_host.copy_(nav_dev, non_blocking=True)
+            stream.wait_event(ev_in[i])
+            if i - 2 in ev_out:
+                stream.wait_event(ev_out[i - 2])         # the navigation buffer of this slot has been read back
+            ukf.predict_update(DT, e2e_in[slot][0].data_ptr(), pkg.POSE_VELOCITY, e2e_in[slot][1].data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
+            ukf.get_navigation_into(e2e_nav[slot].data_ptr(), memspace=pkg.DEVICE)
+            ev_main[i] = torch.cuda.Event()
+            ev_main[i].record(stream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_main[i])
+            e2e_host[slot].copy_(e2e_nav[slot], non_blocking=True)
+            ev_out[i] = torch.cuda.Event()
+            ev_out[i].record(s_out)
+        for d_ in (ev_in, ev_main, ev_out):
+            d_.pop(i - 4, None)
 
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
 
-    def timed(fn):
+    def timed(fn, tail_stream=None):
         for i in range(W):
             fn(i)
         barrier()
@@ -214,6 +243,10 @@ def main():
             for i in range(K):
                 fn(W + i)
                 ev[i + 1].record(stream)
+            if tail_stream is not None:              # e2e: the timed region ends when the last result has reached the host
+                stream.wait_stream(tail_stream)
+                ev[K] = torch.cuda.Event(enable_timing=True)
+                ev[K].record(stream)
         barrier()
         t1 = time.time()
         per = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
@@ -221,7 +254,7 @@ def main():
         return total_ms, per, ukf.kernel_launches - l0, (t0, t1)
 
     tot_ms, per_ms, launches, win = timed(step_resident)
-    e2e_ms, _, e2e_launches, win2 = timed(step_e2e)
+    e2e_ms, _, e2e_launches, win2 = timed(step_e2e, tail_stream=s_out)
     st = ukf.get_status()
     faults = int((st != 0).sum())
 
@@ -252,6 +285,13 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kern_ms = sum(per_ms) / len(per_ms)
+        # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/), valid for the same launch size
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if int(tj.get("filters_per_launch", -1)) == B:
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]) / 1e9, tj.get("source")
         achieved = B_ALG * B / (kern_ms * 1e-3) / 1e9
         value = world * B * K / (tot_ms * 1e-3)
         e2e = world * B * K / (e2e_ms * 1e-3)
@@ -262,11 +302,13 @@ def main():
                            "filters_per_gpu": B, "filters_total": world * B, "dt": DT, "parallelism": f"filters sharded x{world}",
                            "l2": "working set 12.5 GB per GPU >> 126 MB L2 (no flush needed)", "input_ring": NR},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "pose_step_kernel<19,12>",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "pose_fused_kernel<predict, DVL update, 12 warps>",
+                             "traffic_source": traffic_src,
                              "kernel_ms": kern_ms, "alg_bytes_per_filter_step": B_ALG},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * 8, "d2h_bytes_per_step": B * 10 * 8,
                         "ms_per_step": e2e_ms / K,
-                        "what": "pinned-host gyro+DVL -> HBM, fused step, navigation solution (p,q,v) of every filter -> pinned host"},
+                        "what": "per step: pinned-host gyro+DVL -> HBM, fused step through the C ABI, navigation solution (p,q,v) of every "
+                                "filter -> pinned host; copies on side streams overlap the neighbouring steps' kernels"},
                 "gpu_launches": launches, "gpu_launches_e2e": e2e_launches, "clocks": clocks, "filter_faults": faults,
                 "ensemble": {"filters_reduced": n_total, "allreduce_ms": ens_ms}}
         if world == 1 and not args.no_cpu_baseline:
