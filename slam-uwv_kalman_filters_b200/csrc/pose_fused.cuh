@@ -335,16 +335,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const int colane = coloff(lane);
   (void)colane;
 
+  // [mu 54 | pad 2 | panel] is a prefix of the filter block.  It is copied global -> shared asynchronously (cp.async, 16 B per
+  // lane and step, no registers) ONE FILTER AHEAD: the copies for the warp's next filter are issued as soon as the current
+  // panel has been written back, and are waited for at the top of the next iteration, so they fly during the trailing pass.
+  constexpr int NV = (56 + C::PANEL_E) / 2;
+  const unsigned w_saddr = (unsigned)__cvta_generic_to_shared(w);
+  auto fetch_prefix = [&](long long ff) {
+    const char *src = reinterpret_cast<const char *>(a.state + ff * BLK);
+#pragma unroll 4
+    for (int k = lane; k < NV; k += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_saddr + 16u * k), "l"(src + 16 * k) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  {
+    const long long f0 = (long long)blockIdx.x * WARPS + warp;
+    if (f0 < a.B) fetch_prefix(f0);
+  }
+
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
-    // ---- stage mu + panel (a prefix of the block: [mu 54 | pad 2 | panel ...]) -------------------------------
-    {
-      const double2 *src = reinterpret_cast<const double2 *>(blk);
-      double2 *dst = reinterpret_cast<double2 *>(w);
-      constexpr int NV = (56 + C::PANEL_E) / 2;
-#pragma unroll 4
-      for (int k = lane; k < NV; k += 32) dst[k] = __ldcs(src + k);
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
     // prefix of the warp's next filter into L2 now; also fetch the small per-filter inputs early
     {
@@ -790,13 +801,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(w);
-        constexpr int NV = (56 + C::PANEL_E) / 2;
         // if PANEL is odd the last double2 also carries the (unchanged) first trailing entry: it is rewritten by the
         // trailing pass below, which is ordered after this copy by the __syncwarp
 #pragma unroll 4
         for (int k = lane; k < NV; k += 32) __stcs(dst + k, src[k]);
       }
       __syncwarp();
+      {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
+        const long long fn = f + (long long)gridDim.x * WARPS;
+        if (fn < a.B) fetch_prefix(fn);
+      }
       // trailing triangle (columns >= KP): a contiguous suffix of the packed array, streamed HBM -> registers -> HBM in flat
       // order (fully coalesced):  s <- (f_a f_b) s + dt^2 Q_ab - sum_c (K S)_ac K_bc.  f_a f_b and dt^2 Q come from per-CTA
       // tables indexed like the entry, the row/column offsets into the K tables from the LUT; the four water-velocity diagonal
@@ -843,6 +857,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       };
       if (HAS_PREDICT && predicted) pass(std::true_type{});
       else pass(std::false_type{});
+    }
+    else {
+      __syncwarp();
+      const long long fn = f + (long long)gridDim.x * WARPS;
+      if (fn < a.B) fetch_prefix(fn);
     }
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();
