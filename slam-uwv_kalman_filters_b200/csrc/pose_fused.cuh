@@ -137,10 +137,22 @@ __device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *inv
     const double inv = fast_rsqrt3(d);
     a[j] *= inv;                          // lane j: d / sqrt(d) = L[j][j]; lanes > j: L[i][j]
     if (lane < K) Lw[j * LS + lane] = a[j];
-    invd[j] = inv;                        // same value from every lane
+    if (lane == 0) invd[j] = inv;
     __syncwarp();
+    // column j of L back as broadcast loads, two entries per 128-bit load where the (compile-time) offset is 16-byte aligned
+    // (Lw itself is 16-byte aligned: every region of the per-warp layout starts at an even double offset)
+    {
+      constexpr int dummy = 0; (void)dummy;
+      int c = j + 1;
+      if (((j * LS + c) & 1) && c < K) { a[c] = fma(-a[j], Lw[j * LS + c], a[c]); ++c; }
 #pragma unroll
-    for (int c = j + 1; c < K; ++c) a[c] = fma(-a[j], Lw[j * LS + c], a[c]);
+      for (; c + 1 < K; c += 2) {
+        const double2 l2 = *reinterpret_cast<const double2 *>(Lw + j * LS + c);
+        a[c] = fma(-a[j], l2.x, a[c]);
+        a[c + 1] = fma(-a[j], l2.y, a[c + 1]);
+      }
+      if (c < K) a[c] = fma(-a[j], Lw[j * LS + c], a[c]);
+    }
   }
   return ok;
 }
@@ -450,10 +462,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         for (int b = 0; b < KP; ++b) {
           if (b >= 3 && b < 6) continue;
           const int cb = coloff(b);
+          const double fb = ftab[b];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
-            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = fma(FF[cb + x], S[cb + x], Qs[cb + x]);
+            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = fma(rdf[h] * fb, S[cb + x], Qs[cb + x]);
           }
         }
         // orientation rows/cols: T F^T (+ Q cross terms)
