@@ -129,20 +129,24 @@ __device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *inv
   double a[K];
 #pragma unroll
   for (int c = 0; c < K; ++c) a[c] = S[coloff(c) + lane];
+  // the pivots are the critical path (broadcast -> rsqrt -> scale, K times).  Lane i's diagonal entry only ever receives
+  // -L[i][j]^2, products of the lane's OWN column entries, so it is tracked in a register of its own: the next pivot never
+  // waits for the shared-memory round trip that carries the finished column to the other lanes.
+  double dg = S[cidx(lane < K ? lane : 0, lane < K ? lane : 0)];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const double d = bcast(a[j], j);
+    const double d = bcast(dg, j);
     ok = ok && (d > 0.0);
     const double inv = fast_rsqrt3(d);
     a[j] *= inv;                          // lane j: d / sqrt(d) = L[j][j]; lanes > j: L[i][j]
+    dg = fma(-a[j], a[j], dg);            // lanes > j (don't care elsewhere)
     if (lane < K) Lw[j * LS + lane] = a[j];
     if (lane == 0) invd[j] = inv;
     __syncwarp();
     // column j of L back as broadcast loads, two entries per 128-bit load where the (compile-time) offset is 16-byte aligned
     // (Lw itself is 16-byte aligned: every region of the per-warp layout starts at an even double offset)
     {
-      constexpr int dummy = 0; (void)dummy;
       int c = j + 1;
       if (((j * LS + c) & 1) && c < K) { a[c] = fma(-a[j], Lw[j * LS + c], a[c]); ++c; }
 #pragma unroll
@@ -155,6 +159,29 @@ __device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *inv
     }
   }
   return ok;
+}
+
+// G <- G L^-1 with one LANE PER ROW of G (M <= 3 lanes busy) and the whole row in registers: the dependent chain per column
+// is one DMUL + one DFMA instead of a shuffle pair + DMUL + DFMA, and nothing goes through the shuffle network.  Entries of L
+// come in as broadcast loads.  The kernel is bound by dependent-issue latency, so the idle lanes cost nothing.
+template <int K, int M>
+__device__ __forceinline__ void solve_right_rows(double *G, int gs, const double *Lw, const double *invd, int lane) {
+  constexpr int LS = LStride<K>;
+  const int r = lane < M ? lane : 0;
+  double x[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) x[k] = G[r * gs + k];
+#pragma unroll
+  for (int c = K - 1; c >= 0; --c) {
+    x[c] *= invd[c];
+#pragma unroll
+    for (int k = c - 1; k >= 0; --k) x[k] = fma(-x[c], Lw[k * LS + c], x[k]);
+  }
+  if (lane < M) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) G[r * gs + k] = x[k];
+  }
+  __syncwarp();
 }
 
 // G <- G L^-1 (G is M x K, row stride gs; lane = column).  Column c is final once steps K-1..c+1 have been applied; its
@@ -245,7 +272,7 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
     G[2 * KE + j] = 0.5 * (a.z - nz);
   }
   __syncwarp();
-  solve_right_sq<K, 3>(G, KE, Lw, invd, lane);
+  solve_right_rows<K, 3>(G, KE, Lw, invd, lane);
   g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
   return r;
 }
@@ -658,7 +685,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
           __syncwarp();
         }
-        solve_right_sq<K, M>(G, KE, Lw, invd, lane);
+        solve_right_rows<K, M>(G, KE, Lw, invd, lane);
         double T[2][M];
         g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
         if constexpr (NT > 0) {   // + C Sigma[T, x]: panel columns from shared memory, the rest from the trailing triangle
