@@ -129,29 +129,26 @@ __device__ __forceinline__ void cos_sinc_sqrt(double x2, double &c, double &s) {
     s = sn / x;
   } else if (x2 >= 1.220703125e-4) {
     // between MTK's series bound eps^(1/4) = 2^-13 and 1/16 the reference calls cos/sin of sqrt(x2); the Taylor
-    // polynomials below (truncation < 3e-20) return the same doubles to 1 ulp without sqrt / sincos / division
-    double cc = fma(x2, -1.0 / 87178291200.0, 1.0 / 479001600.0);
-    cc = fma(cc, x2, -1.0 / 3628800.0);
-    cc = fma(cc, x2, 1.0 / 40320.0);
-    cc = fma(cc, x2, -1.0 / 720.0);
-    cc = fma(cc, x2, 1.0 / 24.0);
-    cc = fma(cc, x2, -0.5);
-    c = fma(cc, x2, 1.0);
-    double ss = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
-    ss = fma(ss, x2, -1.0 / 39916800.0);
-    ss = fma(ss, x2, 1.0 / 362880.0);
-    ss = fma(ss, x2, -1.0 / 5040.0);
-    ss = fma(ss, x2, 1.0 / 120.0);
-    ss = fma(ss, x2, -1.0 / 6.0);
-    s = fma(ss, x2, 1.0);
+    // polynomials below (truncation < 3e-20) return the same doubles to 1 ulp without sqrt / sincos / division.
+    // Even / odd split (Estrin) in y = x2^2: half the dependent depth of a plain Horner chain.
+    const double y = x2 * x2;
+    double ce = fma(y, 1.0 / 479001600.0, 1.0 / 40320.0);       // x2^2, x2^4, x2^6 terms of cos: 1/24, 1/40320, 1/12!
+    ce = fma(ce, y, 1.0 / 24.0);
+    double co = fma(y, -1.0 / 87178291200.0, -1.0 / 3628800.0);  // x2^1, x2^3, x2^5, x2^7: -1/2, -1/720, -1/10!, -1/14!
+    co = fma(co, y, -1.0 / 720.0);
+    co = fma(co, y, -0.5);
+    c = fma(ce, y, fma(co, x2, 1.0));
+    double se = fma(y, 1.0 / 6227020800.0, 1.0 / 362880.0);      // sinc: 1/120, 1/9!, 1/13!
+    se = fma(se, y, 1.0 / 120.0);
+    double so = fma(y, -1.0 / 1307674368000.0, -1.0 / 39916800.0);   // -1/6, -1/5040, -1/11!, -1/15!
+    so = fma(so, y, -1.0 / 5040.0);
+    so = fma(so, y, -1.0 / 6.0);
+    s = fma(se, y, fma(so, x2, 1.0));
   } else {
-    double cosi = 1., sinc = 1.;
-    double term = -0.5 * x2;
-    cosi += term; term *= (1 / 3.); sinc += term; term *= -(1 / 4.) * x2;
-    cosi += term; term *= (1 / 5.); sinc += term; term *= -(1 / 6.) * x2;
-    cosi += term; term *= (1 / 7.); sinc += term;
-    c = cosi;
-    s = sinc;
+    // MTK's three-term series (cos: 1 - x2/2 + x2^2/24 - x2^3/720, sinc: 1 - x2/6 + x2^2/120 - x2^3/5040) in Horner form:
+    // the same truncated sums to 1 ulp with a third of the dependent depth of the term recurrence
+    c = fma(fma(fma(x2, -1.0 / 720.0, 1.0 / 24.0), x2, -0.5), x2, 1.0);
+    s = fma(fma(fma(x2, -1.0 / 5040.0, 1.0 / 120.0), x2, -1.0 / 6.0), x2, 1.0);
   }
 }
 __device__ __forceinline__ Quat so3_exp(const Vec3 &v, double scale) {
@@ -172,15 +169,17 @@ __device__ __forceinline__ Vec3 so3_log(const Quat &q) {
   if (n2 <= 1.0e-2 * w2) {
     double iw = fast_rcp(q.w);
     double t = n2 * iw * iw;
-    double p = fma(t, -1.0 / 19.0, 1.0 / 17.0);
-    p = fma(p, t, -1.0 / 15.0);
-    p = fma(p, t, 1.0 / 13.0);
-    p = fma(p, t, -1.0 / 11.0);
-    p = fma(p, t, 1.0 / 9.0);
-    p = fma(p, t, -1.0 / 7.0);
-    p = fma(p, t, 1.0 / 5.0);
-    p = fma(p, t, -1.0 / 3.0);
-    p = fma(p, t, 1.0);
+    // atan(x)/x = sum (-t)^k / (2k+1), even / odd split in u = t^2 (half the dependent depth of a Horner chain)
+    const double u = t * t;
+    double pe = fma(u, 1.0 / 17.0, 1.0 / 13.0);      // k = 0, 2, 4, 6, 8
+    pe = fma(pe, u, 1.0 / 9.0);
+    pe = fma(pe, u, 1.0 / 5.0);
+    pe = fma(pe, u, 1.0);
+    double po = fma(u, -1.0 / 19.0, -1.0 / 15.0);    // k = 1, 3, 5, 7, 9
+    po = fma(po, u, -1.0 / 11.0);
+    po = fma(po, u, -1.0 / 7.0);
+    po = fma(po, u, -1.0 / 3.0);
+    const double p = fma(po, t, pe);
     s = 2.0 * iw * p;
   } else {
     double nv = sqrt(n2);

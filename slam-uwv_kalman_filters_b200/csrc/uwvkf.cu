@@ -300,10 +300,10 @@ template <int KMAX, int WARPS>
 int launch_pose(uwvkf_handle h, const pose::Launch &L) {
   using W = pose::WL<KMAX>;
   size_t smem = (size_t)(1432 + 360 + WARPS * W::TOTAL) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one bit per device: the attribute belongs to the device's context
+  if (!(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(pose_step_kernel<KMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set |= 1ull << h->device;
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
@@ -325,12 +325,12 @@ int launch_fused(uwvkf_handle h, const pose::Launch &L) {
   using C = pose::FusedCfg<HP, KIND>;
   constexpr int WARPS = fused_warps<HP, KIND>();
   size_t smem = (size_t)(C::CTA + WARPS * C::TOTAL) * sizeof(double);
-  static bool attr_set = false;
+  static unsigned long long attr_set = 0;   // one bit per device
   uint16_t *lut_dev = nullptr;
   CK(cudaGetSymbolAddress((void **)&lut_dev, g_lut));
-  if (!attr_set) {
+  if (!(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set |= 1ull << h->device;
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
@@ -733,10 +733,10 @@ int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, cons
   if (rc) return rc;
   constexpr int WARPS = 6;
   const size_t smem = (size_t)WARPS * pose::MarkerLayout::TOTAL * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one bit per device
+  if (!(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(pose::pose_marker_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set |= 1ull << h->device;
   }
   const int grid = (int)std::min<long long>((h->B + WARPS - 1) / WARPS, h->sm_count);
   pose::pose_marker_kernel<WARPS><<<grid, WARPS * 32, smem, h->stream>>>(h->d_state, h->d_status, dpx, (const uint8_t *)pv, h->B, M, h->pp);

@@ -17,6 +17,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
@@ -86,6 +87,25 @@ def main():
     timeit("pose update adcp", upd(pkg.POSE_WATER_VELOCITY, d["adcp"], syn.R_ADCP, np.array([0.5])), B, P, ukf)
     timeit("pose fused predict+DVL", lambda: ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
                                                                   syn.R_DVL, memspace=pkg.DEVICE), B, P, ukf)
+    # dense paths (no prefix structure): body efforts (Fossen model per sigma point) and visual markers (59-DOF augmented state)
+    ukf.set_model_parameters(syn.uwv_params_flat())
+    eff = torch.from_numpy(np.tile(np.array([12.0, -3.0, 1.5, 0.0, 0.0, 0.4]), (B, 1))).to(dev)
+    Re = np.diag([4.0] * 3 + [0.25] * 3)
+    timeit("pose update body efforts", upd(pkg.POSE_BODY_EFFORTS, eff, Re), B, P, ukf)
+    timeit("pose update efforts (velocity only)", upd(pkg.POSE_BODY_EFFORTS_VELOCITY_ONLY, eff, Re), B, P, ukf)
+    nav = ukf.get_navigation(0, 1)[0]
+    import structured_ref as sr
+    marker_pose = np.concatenate([nav[0:3] + sr.qrot(nav[3:7], np.array([4.0, 0.3, -0.2])), nav[3:7]])
+    cam_t = nav[0:3] + sr.qrot(nav[3:7], syn.CAM_IN_BODY[0:3]); cam_q = sr.qmul(nav[3:7], syn.CAM_IN_BODY[3:7])
+    px1 = np.zeros((4, 2))
+    for k, ft in enumerate(syn.MARKER_FEATURES):
+        pc = sr.qrot(sr.qconj(cam_q), marker_pose[0:3] + sr.qrot(marker_pose[3:7], ft) - cam_t)
+        px1[k] = [syn.CAMERA[0] * pc[0] / pc[2] + syn.CAMERA[2], syn.CAMERA[1] * pc[1] / pc[2] + syn.CAMERA[3]]
+    pxd = torch.from_numpy(np.tile(px1, (B, 1, 1))).to(dev)
+    pxcov = np.tile(np.array([25.0, 0.0, 0.0, 25.0]), (4, 1))
+    covm = np.diag([4e-2] * 3 + [1e-2] * 3)
+    timeit("pose update visual marker (4 corners)", lambda: ukf.integrate_features(pxd.data_ptr(), pxcov, syn.MARKER_FEATURES, marker_pose, covm, syn.CAMERA,
+                                                                               syn.CAM_IN_BODY, memspace=pkg.DEVICE), B, P, ukf)
     faults = int((ukf.get_status() & ~np.uint32(4)).astype(bool).sum())
     res["pose_faults"] = faults
     ukf.close()
