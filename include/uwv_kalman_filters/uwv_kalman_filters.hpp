@@ -137,6 +137,17 @@ class FilterBase {
   FilterBase(const FilterBase &) = delete;
   FilterBase &operator=(const FilterBase &) = delete;
   void predictionStep(double delta_t) { detail::check(uwvkf_predict(h_, delta_t)); }
+  // Caller-side helper of the base class [pose_estimation, EXT-RECALLED: SURVEY.md 8f-4]: derive delta_t from consecutive sample
+  // times (seconds).  The first call only latches the time; a sample older than the last one, or further ahead than
+  // max_time_delta, is refused (false) and the filter is not stepped.
+  bool predictionStepFromSampleTime(double sample_time, double max_time_delta = 2.0) {
+    if (!have_time_) { last_sample_time_ = sample_time; have_time_ = true; return true; }
+    const double delta = sample_time - last_sample_time_;
+    if (!(delta >= 0.0) || delta > max_time_delta) return false;
+    if (delta > 0.0) predictionStep(delta);
+    last_sample_time_ = sample_time;
+    return true;
+  }
   bool getCurrentState(State &state, int64_t filter = 0) const {
     return uwvkf_get_state(h_, state.data(), nullptr, filter, 1, UWVKF_HOST) == UWVKF_OK;
   }
@@ -161,6 +172,8 @@ class FilterBase {
   }
   uwvkf_handle h_ = nullptr;
   int64_t batch_;
+  double last_sample_time_ = 0.0;
+  bool have_time_ = false;
 };
 
 // ==============================================================================================================
