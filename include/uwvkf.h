@@ -49,7 +49,8 @@ enum uwvkf_error {
   UWVKF_ERR_CUDA = -3,
   UWVKF_ERR_NAN_MEASUREMENT = -4,  /* checkMeasurment() of the reference base class would have thrown */
   UWVKF_ERR_NOT_INITIALIZED = -5,  /* e.g. "Motion model is not initialized!" src/VelocityUKF.cpp:117-118 */
-  UWVKF_ERR_UNSUPPORTED = -6
+  UWVKF_ERR_UNSUPPORTED = -6,
+  UWVKF_ERR_BUSY = -7              /* the sample ring is full */
 };
 
 enum uwvkf_memspace { UWVKF_HOST = 0, UWVKF_DEVICE = 1 };
@@ -210,6 +211,26 @@ int uwvkf_indirect_update_features(uwvkf_handle h, int nfeat, const double *px, 
                                    const double *camera, const double *cam_in_body, const uint8_t *valid, int memspace);
 /* getCorrectedPose (:137-142): out[B][7], host */
 int uwvkf_indirect_get_corrected_pose(uwvkf_handle h, double *out);
+
+/* ---- PoseUKF sample stream: the caller-side loop ------------------------------------------------- */
+/* The reference is driven by an application that, for every arriving sensor sample, calls predictionStepFromSampleTime(ts) and
+ * integrateMeasurement(sample) (Rock task, not in the repository).  A uwvkf_stream is that loop for a batch: timestamped sample
+ * sets are pushed from host memory into a ring of pinned staging buffers + HBM slots (uploaded asynchronously on a copy stream)
+ * and uwvkf_stream_run replays them in time order on the handle's stream -- predictionStep(ts - filter time) fused with the
+ * update into one kernel -- with event dependencies only, so uploads of later samples overlap the kernels of earlier ones and
+ * the host never blocks on the GPU.  kind = a uwvkf_pose_meas vector kind (z[B][m], R[m*m] shared, aux, valid[B] or NULL), or
+ * UWVKF_STREAM_ROTATION_RATE (z[B][3]: the control input of the following predictions, no prediction by itself).  The first
+ * measurement only latches the filter time.  Samples must be pushed in non-decreasing time order. */
+typedef struct uwvkf_stream_s *uwvkf_stream;
+#define UWVKF_STREAM_ROTATION_RATE 100
+int uwvkf_stream_create(uwvkf_handle h, int slots, uwvkf_stream *out);
+int uwvkf_stream_destroy(uwvkf_stream s);
+int uwvkf_stream_push(uwvkf_stream s, double timestamp, int kind, const double *z, const double *R, const double *aux,
+                      const uint8_t *valid);
+/* replays every queued sample set with timestamp <= until; asynchronous (uwvkf_synchronize(h) to wait) */
+int uwvkf_stream_run(uwvkf_stream s, double until);
+int uwvkf_stream_pending(uwvkf_stream s);
+double uwvkf_stream_time(uwvkf_stream s);
 
 /* ---- device-math probe (tests only) ------------------------------------------------------------------- */
 /* Evaluates one device function of the engine per input row on the GPU so that tests can pin the kernels' math against

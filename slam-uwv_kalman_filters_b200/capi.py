@@ -69,6 +69,13 @@ def load_library():
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_stream_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.uwvkf_stream_destroy.argtypes = [C.c_void_p]
+        lib.uwvkf_stream_push.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.uwvkf_stream_run.argtypes = [C.c_void_p, C.c_double]
+        lib.uwvkf_stream_pending.argtypes = [C.c_void_p]
+        lib.uwvkf_stream_time.argtypes = [C.c_void_p]
+        lib.uwvkf_stream_time.restype = C.c_double
         lib.uwvkf_debug_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         vp, ci = C.c_void_p, C.c_int
         lib.uwvkf_velocity_setup_motion_model.argtypes = [vp, vp]
@@ -268,6 +275,44 @@ class IndirectPoseUKFBatch(_FilterBatch):
         out = np.empty((self.batch, 7))
         self._ck(self._lib.uwvkf_indirect_get_corrected_pose(self._h, _ptr(out)))
         return out
+
+
+STREAM_ROTATION_RATE = 100
+
+
+class PoseSampleStream:
+    """Caller-side loop for a PoseUKFBatch (include/uwvkf.h, sample stream): push timestamped sample sets, replay in time order."""
+
+    def __init__(self, ukf, slots=64):
+        self._ukf, self._lib = ukf, ukf._lib
+        self._s = C.c_void_p()
+        ukf._ck(self._lib.uwvkf_stream_create(ukf._h, int(slots), C.byref(self._s)))
+
+    def push(self, timestamp, kind, z, R=None, aux=None, valid=None):
+        self._ukf._ck(self._lib.uwvkf_stream_push(self._s, float(timestamp), int(kind), _ptr(_f64(z)), _ptr(_f64(R)), _ptr(_f64(aux)),
+                                                  _ptr(_u8(valid))))
+
+    def run(self, until=float("inf")):
+        self._ukf._ck(self._lib.uwvkf_stream_run(self._s, float(until)))
+
+    @property
+    def pending(self):
+        return int(self._lib.uwvkf_stream_pending(self._s))
+
+    @property
+    def time(self):
+        return float(self._lib.uwvkf_stream_time(self._s))
+
+    def close(self):
+        if self._s.value:
+            self._lib.uwvkf_stream_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PoseUKFBatch(_FilterBatch):

@@ -745,6 +745,135 @@ int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, cons
   return UWVKF_OK;
 }
 
+/* ---- sample stream (the caller-side loop) ------------------------------------------------------------------ */
+struct uwvkf_stream_s {
+  uwvkf_handle h = nullptr;
+  int slots = 0, head = 0, count = 0;        // ring: [head, head + count) are queued and not yet replayed
+  cudaStream_t copy = nullptr;
+  double t_filter = 0.0;
+  bool have_time = false;
+  struct Slot {
+    double ts = 0.0;
+    int kind = 0;
+    double R[pose::MAXM * pose::MAXM] = {0}, aux[4] = {0};
+    bool has_aux = false, has_valid = false, used = false;
+    double *h_z = nullptr, *d_z = nullptr;   // pinned staging / HBM, [B][MAXM]
+    uint8_t *h_v = nullptr, *d_v = nullptr;  // [B]
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+  };
+  std::vector<Slot> ring;
+};
+
+int uwvkf_stream_create(uwvkf_handle h, int slots, uwvkf_stream *out) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!out || slots < 2 || slots > 4096) return fail(UWVKF_ERR_INVALID_ARGUMENT, "2 <= slots <= 4096");
+  uwvkf_stream s = new uwvkf_stream_s();
+  s->h = h; s->slots = slots; s->ring.resize(slots);
+  cudaError_t e = cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking);
+  const size_t zb = (size_t)h->B * pose::MAXM * sizeof(double);
+  for (auto &sl : s->ring) {
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_z, zb);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_z, zb);
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_v, (size_t)h->B);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_v, (size_t)h->B);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    uwvkf_stream_destroy(s);
+    return fail(UWVKF_ERR_CUDA, "stream allocation failed: " + msg);
+  }
+  *out = s;
+  return UWVKF_OK;
+}
+
+int uwvkf_stream_destroy(uwvkf_stream s) {
+  if (!s) return UWVKF_OK;
+  cudaSetDevice(s->h->device);
+  if (s->copy) cudaStreamSynchronize(s->copy);
+  cudaStreamSynchronize(s->h->stream);
+  for (auto &sl : s->ring) {
+    cudaFreeHost(sl.h_z); cudaFree(sl.d_z); cudaFreeHost(sl.h_v); cudaFree(sl.d_v);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+    if (sl.consumed) cudaEventDestroy(sl.consumed);
+  }
+  if (s->copy) cudaStreamDestroy(s->copy);
+  delete s;
+  return UWVKF_OK;
+}
+
+int uwvkf_stream_pending(uwvkf_stream s) { return s ? s->count : 0; }
+double uwvkf_stream_time(uwvkf_stream s) { return s ? s->t_filter : 0.0; }
+
+int uwvkf_stream_push(uwvkf_stream s, double timestamp, int kind, const double *z, const double *R, const double *aux,
+                      const uint8_t *valid) {
+  if (!s) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null stream");
+  uwvkf_handle h = s->h;
+  CK(cudaSetDevice(h->device));
+  const int m = kind == UWVKF_STREAM_ROTATION_RATE ? 3 : meas_dim(kind);
+  if (m < 0 || !z || std::isnan(timestamp)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad sample");
+  if (kind != UWVKF_STREAM_ROTATION_RATE && !R) return fail(UWVKF_ERR_INVALID_ARGUMENT, "R must not be NULL");
+  if (s->count == s->slots) return fail(UWVKF_ERR_BUSY, "sample ring is full: call uwvkf_stream_run");
+  if (s->count > 0) {
+    const auto &last = s->ring[(s->head + s->count - 1) % s->slots];
+    if (timestamp < last.ts) return fail(UWVKF_ERR_INVALID_ARGUMENT, "samples must be pushed in time order");
+  } else if (s->have_time && timestamp < s->t_filter) {
+    return fail(UWVKF_ERR_INVALID_ARGUMENT, "sample is older than the filter time");
+  }
+  auto &sl = s->ring[(s->head + s->count) % s->slots];
+  if (sl.used) CK(cudaEventSynchronize(sl.copied));   // the staging buffer's previous upload must have left the host
+  const size_t n = (size_t)h->B * m;
+  for (size_t k = 0; k < n; ++k) {
+    if (std::isnan(z[k]) && h->B <= 1024) return fail(UWVKF_ERR_NAN_MEASUREMENT, "sample contains NaN");   // checkMeasurment()
+    sl.h_z[k] = z[k];
+  }
+  sl.ts = timestamp; sl.kind = kind;
+  if (R) for (int k = 0; k < m * m; ++k) { if (std::isnan(R[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "R contains NaN"); sl.R[k] = R[k]; }
+  sl.has_aux = aux != nullptr;
+  if (aux) {
+    const int na = (kind == UWVKF_POSE_WATER_VELOCITY) ? 1 : (kind == UWVKF_POSE_DELAYED_XY ? 2 : 3);
+    for (int k = 0; k < na; ++k) sl.aux[k] = aux[k];
+  }
+  sl.has_valid = valid != nullptr;
+  if (valid) std::memcpy(sl.h_v, valid, (size_t)h->B);
+  // the HBM copy of this slot may still be read by kernels of an earlier lap of the ring: order the upload behind them
+  if (sl.used) CK(cudaStreamWaitEvent(s->copy, sl.consumed, 0));
+  CK(cudaMemcpyAsync(sl.d_z, sl.h_z, n * sizeof(double), cudaMemcpyHostToDevice, s->copy));
+  if (valid) CK(cudaMemcpyAsync(sl.d_v, sl.h_v, (size_t)h->B, cudaMemcpyHostToDevice, s->copy));
+  CK(cudaEventRecord(sl.copied, s->copy));
+  sl.used = true;
+  s->count++;
+  return UWVKF_OK;
+}
+
+int uwvkf_stream_run(uwvkf_stream s, double until) {
+  if (!s) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null stream");
+  uwvkf_handle h = s->h;
+  CK(cudaSetDevice(h->device));
+  while (s->count > 0) {
+    auto &sl = s->ring[s->head];
+    if (sl.ts > until) break;
+    CK(cudaStreamWaitEvent(h->stream, sl.copied, 0));
+    int rc = UWVKF_OK;
+    if (sl.kind == UWVKF_STREAM_ROTATION_RATE) {
+      rc = uwvkf_pose_set_rotation_rate(h, sl.d_z, UWVKF_DEVICE);          // control input of the following predictions
+    } else {
+      const double dt = s->have_time ? sl.ts - s->t_filter : 0.0;          // predictionStepFromSampleTime: the first sample latches
+      const double *aux = sl.has_aux ? sl.aux : nullptr;
+      const uint8_t *v = sl.has_valid ? sl.d_v : nullptr;
+      if (dt > 0.0) rc = uwvkf_pose_predict_update(h, dt, nullptr, sl.kind, sl.d_z, sl.R, 0, aux, v, UWVKF_DEVICE);
+      else rc = uwvkf_pose_update(h, sl.kind, sl.d_z, sl.R, 0, aux, v, UWVKF_DEVICE);
+      if (rc == UWVKF_OK) { s->t_filter = sl.ts; s->have_time = true; }
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(sl.consumed, h->stream));
+    s->head = (s->head + 1) % s->slots;
+    s->count--;
+  }
+  return UWVKF_OK;
+}
+
 int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace) {
   REQUIRE(h, UWVKF_FILTER_POSE);
   if (!out || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");

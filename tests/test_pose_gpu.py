@@ -284,6 +284,50 @@ def test_visual_marker_update_parity(pkg, syn, scen):
     ukf.close()
 
 
+def test_sample_stream_replays_like_direct_calls(pkg, syn, scen):
+    """The caller-side loop (uwvkf_stream_*): timestamped gyro / DVL / acceleration / pressure sample sets pushed from host memory
+    through a small ring and replayed in time order == the same sequence issued call by call."""
+    B, STEPS = 16, 25
+    a, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    b, *_ = make_batch(pkg, syn, scen, B)
+    stream = pkg.PoseSampleStream(a, slots=8)
+    t0 = 100.0
+    for s in range(0, STEPS + 1):
+        inp = syn.pose_inputs(filt, max(s, 1))
+        t = t0 + s * DT
+        valid = (np.arange(B) + s) % 4 != 0
+        samples = [(pkg.STREAM_ROTATION_RATE, inp["gyro"], None, None, None),
+                   (pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, None, valid),
+                   (pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC, None, None)]
+        if s % 10 == 0:
+            samples.append((pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE, np.array([0.3, -0.1, 0.2]), None))
+        for kind, z, R, aux, v in samples:
+            stream.push(t, kind, z, R, aux, v)
+            if stream.pending >= 6:          # the ring has 8 slots: drain before it fills
+                stream.run()
+        # the same thing call by call: the first measurement of a new timestamp carries the prediction step
+        b.integrate_rotation_rate(inp["gyro"])
+        if s == 0:
+            b.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, valid=valid)
+        else:
+            b.predict_update(DT, None, pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, valid=valid)
+        b.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+        if s % 10 == 0:
+            b.integrate_measurement(pkg.POSE_PRESSURE, inp["pressure"], syn.R_PRESSURE, aux=np.array([0.3, -0.1, 0.2]))
+    stream.run(t0 + (STEPS - 1) * DT)        # replay up to the second-to-last timestamp only
+    assert stream.pending > 0 and abs(stream.time - (t0 + (STEPS - 1) * DT)) < 1e-12
+    stream.run()
+    assert stream.pending == 0 and abs(stream.time - (t0 + STEPS * DT)) < 1e-9
+    with pytest.raises(pkg.UwvkfError):      # time must not run backwards
+        stream.push(t0, pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    # predict dt: the stream derives it from timestamps (t0 + s DT differences), the direct path passes DT itself
+    assert np.abs(ma - mb).max() < 1e-9 and np.abs(ca - cb).max() < 1e-9 * np.abs(cb).max()
+    assert not a.get_status().any() and not b.get_status().any()
+    stream.close(); a.close(); b.close()
+
+
 def test_lockstep_sequence_parity(pkg, syn, scen):
     """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
     step so that the asserted error is the per-step error of north_star."""
