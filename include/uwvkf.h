@@ -122,6 +122,9 @@ int uwvkf_set_process_noise(uwvkf_handle h, const double *Q);
 /* ukfom mean-iteration policy: loop while |mean_delta| > tol and fewer than max_it passes (default 1e-9, 100) */
 int uwvkf_set_mean_policy(uwvkf_handle h, double tol, int max_it);
 int uwvkf_get_status(uwvkf_handle h, uint32_t *status, int64_t first, int64_t count);
+/* metrics: counts[4] = number of filters whose status has UWVKF_ST_NOT_SPD / NAN_MEASUREMENT / GATE_REJECTED /
+ * MEAN_NOT_CONVERGED set (the reference only writes such events to stderr) */
+int uwvkf_status_counts(uwvkf_handle h, int64_t *counts);
 int uwvkf_clear_status(uwvkf_handle h);
 
 /* ---- PoseUKF -------------------------------------------------------------------------------------- */

@@ -56,6 +56,7 @@ def load_library():
         lib.uwvkf_set_process_noise.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_set_mean_policy.argtypes = [C.c_void_p, C.c_double, C.c_int]
         lib.uwvkf_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        lib.uwvkf_status_counts.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_pose_set_params.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_pose_set_model_parameters.argtypes = [C.c_void_p, C.c_void_p]
         lib.uwvkf_pose_set_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
@@ -183,6 +184,12 @@ class _FilterBatch:
         st = np.empty(count, dtype=np.uint32)
         self._ck(self._lib.uwvkf_get_status(self._h, _ptr(st), first, count))
         return st
+
+    def status_counts(self):
+        """{bit name: number of filters with that status bit set} (device-side reduction)."""
+        c = np.zeros(4, dtype=np.int64)
+        self._ck(self._lib.uwvkf_status_counts(self._h, _ptr(c)))
+        return dict(zip(("not_spd", "nan_measurement", "gate_rejected", "mean_not_converged"), (int(x) for x in c)))
 
     def clear_status(self):
         self._ck(self._lib.uwvkf_clear_status(self._h))

@@ -178,6 +178,22 @@ __global__ void debug_eval_kernel(int what, const double *in, double *out, int n
   if (act) for (int k = 0; k < 4; ++k) out[(size_t)i * 4 + k] = o[k];
 }
 
+// number of filters with each status bit set (metrics: non-SPD, NaN-refused, gate-rejected, mean-not-converged)
+__global__ void status_count_kernel(const uint32_t *status, long long B, unsigned long long *out) {
+  unsigned c[4] = {0, 0, 0, 0};
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
+    const uint32_t s = status[f];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] += (s >> k) & 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned v = c[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, (unsigned long long)v);
+  }
+}
+
 // ensemble statistics: out = [count, sum mu (DIM), sum mu mu^T (lower, row-major packed)]
 template <int DIM>
 __global__ void ensemble_stats_kernel(const double *state, long long stride, long long B, double *out) {
@@ -596,6 +612,21 @@ int uwvkf_get_status(uwvkf_handle h, uint32_t *status, int64_t first, int64_t co
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(status, h->d_status + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return UWVKF_OK;
+}
+int uwvkf_status_counts(uwvkf_handle h, int64_t *counts) {
+  if (!h || !counts) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_tmp(h, 4 * sizeof(unsigned long long));
+  if (rc) return rc;
+  unsigned long long *d = reinterpret_cast<unsigned long long *>(h->d_tmp), hc[4];
+  CK(cudaMemsetAsync(d, 0, sizeof hc, h->stream));
+  status_count_kernel<<<std::max(1, std::min(h->sm_count * 4, (int)((h->B + 255) / 256))), 256, 0, h->stream>>>(h->d_status, h->B, d);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaMemcpyAsync(hc, d, sizeof hc, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 4; ++k) counts[k] = (int64_t)hc[k];
   return UWVKF_OK;
 }
 int uwvkf_clear_status(uwvkf_handle h) {

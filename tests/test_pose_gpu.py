@@ -401,6 +401,7 @@ def test_gate_rejects_outlier(pkg, syn, scen):
     gmu, gcov = ukf.get_state()
     st = ukf.get_status()
     assert (st[::2] & pkg.ST_GATE_REJECTED).all() and not (st[1::2] & pkg.ST_GATE_REJECTED).any()
+    assert ukf.status_counts() == {"not_spd": 0, "nan_measurement": 0, "gate_rejected": B // 2, "mean_not_converged": 0}
     assert np.array_equal(gmu[::2], mu[::2]) and np.array_equal(gcov[::2], cov[::2])
     assert not np.array_equal(gmu[1::2], mu[1::2])
     ukf.clear_status()
