@@ -235,6 +235,19 @@ int uwvkf_stream_run(uwvkf_stream s, double until);
 int uwvkf_stream_pending(uwvkf_stream s);
 double uwvkf_stream_time(uwvkf_stream s);
 
+/* ---- CUDA-graph replay of a fixed schedule ------------------------------------------------------------- */
+/* Every step / update entry point called with memspace = UWVKF_DEVICE only enqueues work on the handle's stream, so a fixed
+ * schedule (e.g. K steps of rotation rate + fused predict/DVL + acceleration reading consecutive rows of device-resident input
+ * arrays) can be captured once and replayed with one launch: uwvkf_graph_begin(h); <calls>; uwvkf_graph_end(h, &g);
+ * uwvkf_graph_launch(g) as often as needed (the inputs are read from the same device addresses at every replay).  The handle
+ * needs a user stream (uwvkf_set_stream) and every kernel of the schedule must have been launched once before the capture.
+ * Calls that return data to the host or take host pointers cannot be captured. */
+typedef struct uwvkf_graph_s *uwvkf_graph;
+int uwvkf_graph_begin(uwvkf_handle h);
+int uwvkf_graph_end(uwvkf_handle h, uwvkf_graph *out);
+int uwvkf_graph_launch(uwvkf_graph g);
+int uwvkf_graph_destroy(uwvkf_graph g);
+
 /* ---- device-math probe (tests only) ------------------------------------------------------------------- */
 /* Evaluates one device function of the engine per input row on the GPU so that tests can pin the kernels' math against
  * the oracle / high-precision values: in[n][8] -> out[n][4] (host pointers, PoseUKF handle with parameters set).

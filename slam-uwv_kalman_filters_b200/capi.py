@@ -77,6 +77,10 @@ def load_library():
         lib.uwvkf_stream_pending.argtypes = [C.c_void_p]
         lib.uwvkf_stream_time.argtypes = [C.c_void_p]
         lib.uwvkf_stream_time.restype = C.c_double
+        lib.uwvkf_graph_begin.argtypes = [C.c_void_p]
+        lib.uwvkf_graph_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.uwvkf_graph_launch.argtypes = [C.c_void_p]
+        lib.uwvkf_graph_destroy.argtypes = [C.c_void_p]
         lib.uwvkf_debug_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         vp, ci = C.c_void_p, C.c_int
         lib.uwvkf_velocity_setup_motion_model.argtypes = [vp, vp]
@@ -143,6 +147,21 @@ class _FilterBatch:
             self.close()
         except Exception:
             pass
+
+    def graph_begin(self):
+        """Start capturing the DEVICE-memspace calls that follow into a CUDA graph (the handle needs a user stream)."""
+        self._ck(self._lib.uwvkf_graph_begin(self._h))
+
+    def graph_end(self):
+        g = C.c_void_p()
+        self._ck(self._lib.uwvkf_graph_end(self._h, C.byref(g)))
+        return g
+
+    def graph_launch(self, g):
+        self._ck(self._lib.uwvkf_graph_launch(g))
+
+    def graph_destroy(self, g):
+        self._lib.uwvkf_graph_destroy(g)
 
     def synchronize(self):
         self._ck(self._lib.uwvkf_synchronize(self._h))

@@ -29,7 +29,8 @@ struct uwvkf_filter_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
-  int64_t launches = 0;
+  int64_t launches = 0, launches_at_capture = 0;
+  bool capturing = false;
   uint32_t *d_status = nullptr;
   double mean_tol = 1e-9;
   int mean_max_it = 100;

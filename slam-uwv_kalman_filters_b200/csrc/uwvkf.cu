@@ -905,6 +905,62 @@ int uwvkf_stream_run(uwvkf_stream s, double until) {
   return UWVKF_OK;
 }
 
+/* ---- CUDA-graph execution of a repeating schedule --------------------------------------------------------- */
+struct uwvkf_graph_s {
+  uwvkf_handle h = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches_per_replay = 0;
+};
+
+int uwvkf_graph_begin(uwvkf_handle h) {
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (!h->stream) return fail(UWVKF_ERR_INVALID_ARGUMENT, "graph capture needs a user stream (uwvkf_set_stream): the legacy default stream cannot be captured");
+  if (h->capturing) return fail(UWVKF_ERR_INVALID_ARGUMENT, "a capture is already in progress");
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+  h->capturing = true;
+  h->launches_at_capture = h->launches;
+  return UWVKF_OK;
+}
+
+int uwvkf_graph_end(uwvkf_handle h, uwvkf_graph *out) {
+  if (!h || !out) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (!h->capturing) return fail(UWVKF_ERR_INVALID_ARGUMENT, "no capture in progress");
+  h->capturing = false;
+  uwvkf_graph g = new uwvkf_graph_s();
+  g->h = h;
+  g->launches_per_replay = h->launches - h->launches_at_capture;
+  h->launches = h->launches_at_capture;                       // nothing ran during the capture
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    cudaGetLastError();
+    uwvkf_graph_destroy(g);
+    return fail(UWVKF_ERR_CUDA, "graph capture failed (only calls with memspace = UWVKF_DEVICE can be captured): " + msg);
+  }
+  *out = g;
+  return UWVKF_OK;
+}
+
+int uwvkf_graph_launch(uwvkf_graph g) {
+  if (!g || !g->exec) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null graph");
+  CK(cudaSetDevice(g->h->device));
+  CK(cudaGraphLaunch(g->exec, g->h->stream));
+  g->h->launches += g->launches_per_replay;
+  return UWVKF_OK;
+}
+
+int uwvkf_graph_destroy(uwvkf_graph g) {
+  if (!g) return UWVKF_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return UWVKF_OK;
+}
+
 int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace) {
   REQUIRE(h, UWVKF_FILTER_POSE);
   if (!out || first < 0 || count <= 0 || first + count > h->B) return fail(UWVKF_ERR_INVALID_ARGUMENT, "bad arguments");

@@ -328,6 +328,52 @@ def test_sample_stream_replays_like_direct_calls(pkg, syn, scen):
     stream.close(); a.close(); b.close()
 
 
+def test_cuda_graph_replay_of_a_schedule(pkg, syn, scen):
+    """A K-step schedule (rotation rate + fused predict/DVL + acceleration per step, inputs resident in HBM) captured once into a
+    CUDA graph and replayed == the same calls issued one by one."""
+    import torch
+    B, K = 32, 6
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    filt = np.arange(B)
+    mu, cov = syn.pose_initial_batch(filt, scen["cfg"])
+    mk = lambda: pkg.PoseUKFBatch(B, scen["par"], stream=stream.cuda_stream)
+    a, b = mk(), mk()
+    for u in (a, b):
+        u.set_process_noise(scen["Q"]); u.set_state(mu, cov)
+    inputs = [syn.pose_inputs(filt, s) for s in range(1, K + 1)]
+    gy = torch.from_numpy(np.stack([i["gyro"] for i in inputs])).to(dev)
+    dv = torch.from_numpy(np.stack([i["dvl"] for i in inputs])).to(dev)
+    ac = torch.from_numpy(np.stack([i["acc"] for i in inputs])).to(dev)
+    torch.cuda.synchronize()
+
+    def schedule(u):
+        for k in range(K):
+            u.predict_update(DT, gy[k].data_ptr(), pkg.POSE_VELOCITY, dv[k].data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
+            u.integrate_measurement(pkg.POSE_ACCELERATION, ac[k].data_ptr(), syn.R_ACC, memspace=pkg.DEVICE)
+
+    schedule(b)                      # reference: call by call (also warms up every kernel of the schedule on this device)
+    schedule(b)
+    b.synchronize()
+    n0 = a.kernel_launches
+    a.graph_begin()
+    schedule(a)
+    g = a.graph_end()
+    assert a.kernel_launches == n0, "nothing runs while capturing"
+    ma0, _ = a.get_state()
+    assert np.array_equal(ma0, mu)
+    a.graph_launch(g)
+    a.graph_launch(g)
+    a.synchronize()
+    assert a.kernel_launches == n0 + 2 * 2 * K + 1      # 2 replays x (fused step + update) x K, + the getter above
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    assert not a.get_status().any()
+    a.graph_destroy(g)
+    a.close(); b.close()
+
+
 def test_lockstep_sequence_parity(pkg, syn, scen):
     """100 Hz predict + accelerometer + DVL, pressure and ADCP at 10 Hz; GPU and oracle are re-synchronised every
     step so that the asserted error is the per-step error of north_star."""
