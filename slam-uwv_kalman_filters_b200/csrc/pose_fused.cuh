@@ -20,17 +20,25 @@ namespace pose {
 constexpr int M_NONE = -1;
 
 // Measurement traits of the fused kernel: prefix K (tangent coordinates the model reads arbitrarily) plus an AFFINE TAIL
-// of NT consecutive tangent coordinates T0..T0+NT-1 (all >= K) that the model reads affinely once the prefix is fixed.
+// of NT tangent coordinates tail(0..NT-1) (ascending, all >= K) that the model reads affinely once the prefix is fixed
+// (slot(t) maps a tail coordinate back to its position in that list).
 // Sigma columns j >= K move only the tail, Z_j(+-) = Z_0 +- C L[T, j], so their sums collapse to Schur complements
 // (tests/structured_ref.py::pose_update_tail states the algebra):
 //   S_zz = 1/2 sum_{centre, j<K} w dz dz^T + C (Sigma_TT - L_T L_T^T) C^T + R,
 //   P_xz = Sigma[:, :K] L11^-T (B - L_T^T C^T) + Sigma[:, T] C^T,         L_T = Sigma[T, :K] L11^-T.
 template <int KIND> struct FMeas : Meas<KIND> {
-  static constexpr int NT = 0, T0 = 0;
+  static constexpr int NT = 0;
+  __host__ __device__ static constexpr int tail(int) { return 0; }
+  __host__ __device__ static constexpr int slot(int) { return 0; }
   __device__ static void tail_jac(const double *, const double *, const Params &, double *) {}
 };
+// (The accelerometer model q^-1 (a + g e_z) + b_a also fits this form -- prefix 6, tail = acceleration, bias, gravity -- and
+// was measured: parity green, but the 7-coordinate tail (49 Sigma_TT entries, 14 trailing-triangle loads per lane in the middle
+// of the critical path) costs what the smaller Cholesky saves, 2.12 ms vs 2.08 ms per 262,144 filters, so it stays prefix 19.)
 template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, q, gravity) = 19, tail = water density
-  static constexpr int K = 19, M = 1, NT = 1, T0 = T_RHO;
+  static constexpr int K = 19, M = 1, NT = 1;
+  __host__ __device__ static constexpr int tail(int) { return T_RHO; }
+  __host__ __device__ static constexpr int slot(int) { return 0; }
   template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
     Meas<M_PRESSURE>::eval(mu, d, aux, P, o);
   }
@@ -40,7 +48,9 @@ template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, 
   }
 };
 template <> struct FMeas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151: prefix (q, v) = 9, tail = wv, wv_below, bias_adcp
-  static constexpr int K = 9, M = 2, NT = 6, T0 = T_WV;
+  static constexpr int K = 9, M = 2, NT = 6;
+  __host__ __device__ static constexpr int tail(int r) { return T_WV + r; }
+  __host__ __device__ static constexpr int slot(int t) { return t - T_WV; }
   template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
     Meas<M_WATER_VELOCITY>::eval(mu, d, aux, P, o);
   }
@@ -531,9 +541,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== update (k = Meas::K) + apply_delta (k = 6) ==========================
     if constexpr (KIND != M_NONE) {
       using MM = FMeas<KIND>;
-      constexpr int K = MM::K, M = MM::M, NT = MM::NT, T0 = MM::T0;
+      constexpr int K = MM::K, M = MM::M, NT = MM::NT;
       constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
-      static_assert(NT == 0 || (T0 >= C::KP && K <= 32), "the affine tail must lie outside the panel");
+      static_assert(NT == 0 || (MM::tail(0) >= K && K <= 32), "tail coordinates lie behind the prefix");
       // entry (ta, tb), ta >= tb >= KP, of the covariance the update works on: the trailing triangle still holds the
       // pre-predict values in HBM, so the process map is applied on the fly (same expression as the write-back pass)
       auto trailing = [&](int ta, int tb) {
@@ -545,6 +555,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         }
         return sv;
       };
+      // entry (ta, tb), ta >= tb, wherever it lives: the panel in shared memory (column tb < KP) or the trailing triangle
+      auto sig = [&](int ta, int tb) { return tb < C::KP ? S[coloff(tb) + ta] : trailing(ta, tb); };
+      (void)sig;
       bool go = !(opu.valid && !opu.valid[f]);
       double z[M], Rm[M * M];
       if (go) {
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         double lt[NT > 0 ? NT : 1];   // lane j < K: L[T0 + r][j], rows T of the panel factor Sigma[:, :K] L11^-T
         if constexpr (NT > 0) {
 #pragma unroll
-          for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? S[coloff(lane) + T0 + r] : 0.0;
+          for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? S[coloff(lane) + MM::tail(r)] : 0.0;
           for (int k = 0; k < K; ++k) {   // forward substitution, one column of L11 per step
             const double ik = invd[k];
             const double l = (lane > k && lane < K) ? Lw[k * LStride<K> + lane] : 0.0;
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           const int j = (p - 1) >> 1;
           const double sg = (p & 1) ? 1.0 : -1.0;
           auto d = [&](int t) {
-            if (NT > 0 && t >= K) return on ? sg * LTs[(t - T0) * KE + j] : 0.0;   // t is a literal: resolved at compile time
+            if (NT > 0 && t >= K) return on ? sg * LTs[MM::slot(t) * KE + j] : 0.0;   // t is a literal: resolved at compile time
             return (on && t >= j) ? sg * Lw[j * LStride<K> + (t < K ? t : 0)] : 0.0;
           };
           MM::eval(mu, d, opu.aux, P, Z[r]);
@@ -662,7 +675,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
           for (int a2 = 0; a2 < NT; ++a2)
 #pragma unroll
-            for (int b2 = 0; b2 <= a2; ++b2) stt[a2 * NT + b2] = stt[b2 * NT + a2] = trailing(T0 + a2, T0 + b2);
+            for (int b2 = 0; b2 <= a2; ++b2) stt[a2 * NT + b2] = stt[b2 * NT + a2] = sig(MM::tail(a2), MM::tail(b2));
 #pragma unroll
           for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -695,8 +708,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (x < N) {
 #pragma unroll
               for (int r = 0; r < NT; ++r) {
-                const int t = T0 + r;
-                const double sx = (x < C::KP) ? S[coloff(x) + t] : (x <= t ? trailing(t, x) : trailing(x, t));
+                const int t = MM::tail(r);
+                const double sx = x <= t ? sig(t, x) : sig(x, t);
 #pragma unroll
                 for (int c = 0; c < M; ++c) T[h][c] = fma(Ct[c * NT + r], sx, T[h][c]);
               }
