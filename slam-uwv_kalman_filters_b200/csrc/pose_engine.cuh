@@ -124,25 +124,40 @@ __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double
     __syncwarp();
     return ok;
   } else {
-    // general path (K up to N): right-looking factorisation in shared memory
-    constexpr int LP = K * (K + 1) / 2;
-    for (int j = 0; j < K; ++j)
-      for (int i = j + lane; i < K; i += 32) Lw[lidx<K>(i, j)] = S[cidx(i, j)];
-    (void)LP;
-    __syncwarp();
+    // general path (K up to N): left-looking factorisation, lanes own rows (i = lane + 32 h); column j of L is
+    //   L[i][j] = (Sigma[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j]
+    // with L[j][k] a broadcast load.  One barrier per column and a third of the shared-memory traffic of the right-looking
+    // form (which re-writes the whole trailing block for every column).
+    constexpr int RND = (K + 31) / 32;
     bool ok = true;
     for (int j = 0; j < K; ++j) {
-      double d = Lw[lidx<K>(j, j)];
-      ok = ok && (d > 0.0);
-      double inv = rsqrt(d);
-      __syncwarp();
-      for (int i = j + 1 + lane; i < K; i += 32) Lw[lidx<K>(i, j)] *= inv;
-      if (lane == 0) { Lw[lidx<K>(j, j)] = d * inv; invd[j] = inv; }
-      __syncwarp();
-      for (int c = j + 1; c < K; ++c) {
-        double lcj = Lw[lidx<K>(c, j)];
-        for (int i = c + lane; i < K; i += 32) Lw[lidx<K>(i, c)] = fma(-Lw[lidx<K>(i, j)], lcj, Lw[lidx<K>(i, c)]);
+      double sacc[RND];
+#pragma unroll
+      for (int h = 0; h < RND; ++h) {
+        const int i = lane + 32 * h;
+        double acc = 0.0;
+        if (i >= j && i < K) {
+          acc = S[cidx(i, j)];
+          int ei = lidx<K>(i, 0), ej = lidx<K>(j, 0);
+          for (int k = 0; k < j; ++k) {
+            acc = fma(-Lw[ei], Lw[ej], acc);
+            ei += K - k - 1; ej += K - k - 1;          // lidx(i, k + 1) - lidx(i, k)
+          }
+        }
+        sacc[h] = acc;
       }
+      double dsel = sacc[0];
+#pragma unroll
+      for (int h = 1; h < RND; ++h) if ((j >> 5) == h) dsel = sacc[h];
+      const double d = __shfl_sync(kFull, dsel, j & 31);
+      ok = ok && (d > 0.0);
+      const double inv = rsqrt(d);
+#pragma unroll
+      for (int h = 0; h < RND; ++h) {
+        const int i = lane + 32 * h;
+        if (i >= j && i < K) Lw[lidx<K>(i, j)] = sacc[h] * inv;
+      }
+      if (lane == 0) invd[j] = inv;
       __syncwarp();
     }
     return ok;
