@@ -57,7 +57,17 @@ __device__ __forceinline__ bool chol_aug(const double *A, double *L, int lane) {
       double acc = 0.0;
       if (i >= j && i < NA) {
         acc = A[aidx(i, j)];
-        for (int k = 0; k < j; ++k) acc = fma(-L[aidx(i, k)], L[aidx(j, k)], acc);
+        int ei = i, ej = j;                              // aidx(i, 0), aidx(j, 0); aidx(., k + 1) - aidx(., k) = NA - k - 1
+        double acc2 = 0.0;                               // two partial sums: half the dependent depth
+        int k = 0;
+        for (; k + 1 < j; k += 2) {
+          acc = fma(-L[ei], L[ej], acc);
+          const int st1 = NA - k - 1;
+          acc2 = fma(-L[ei + st1], L[ej + st1], acc2);
+          ei += 2 * NA - 2 * k - 3; ej += 2 * NA - 2 * k - 3;
+        }
+        if (k < j) acc = fma(-L[ei], L[ej], acc);
+        acc += acc2;
       }
       s[h] = acc;
     }
@@ -207,9 +217,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_marker_kernel(double *stat
         const int x = lane + 32 * h;
         if (x < NA) {
           double p0 = 0, p1 = 0;
+          int e = x;                                       // aidx(x, 0)
           for (int j = 0; j <= x; ++j) {
-            const double l = L[aidx(x, j)];
+            const double l = L[e];
             p0 = fma(l, PB[j], p0); p1 = fma(l, PB[60 + j], p1);
+            e += NA - j - 1;
           }
           const double k0 = p0 * Si[0] + p1 * Si[2], k1 = p0 * Si[1] + p1 * Si[3];
           KG[x] = k0; KG[60 + x] = k1;
@@ -295,8 +307,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_marker_kernel(double *stat
         const bool isvec = x < NA && !(x >= 3 && x < 6) && x < TA_MQ;
         if (isvec) {
           double acc[6] = {0, 0, 0, 0, 0, 0};
-          for (int j = 0; j <= x; ++j) {
-            const double l = L[aidx(x, j)];
+          int e = x;
+          for (int j = 0; j <= x; e += NA - j - 1, ++j) {
+            const double l = L[e];
 #pragma unroll
             for (int c = 0; c < 6; ++c) acc[c] = fma(l, PB[c * 60 + j], acc[c]);
           }
