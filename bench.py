@@ -27,6 +27,10 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 DT = 0.01
 B_ALG = 23760.0          # algorithmic HBM bytes per filter-step: read + write of mu (54) and packed Sigma (1431) doubles
+W_ALG = 1.0e6            # FP64 flop per filter-step of the REFERENCE algorithm (symmetric-minimal count)
+W_EXEC = 1.424e5         # FP64 flop per filter-step the fused kernel executes (ncu: 32 x (2 DFMA + DMUL + DADD) + 512 per DMMA,
+                         # profiles/r1_v4_pose_fused_kernel_1M.txt): the prefix-structured transform does 7x less arithmetic
+FP64_PEAK = 36.9e12      # measured DFMA peak of this pool's B200 (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)
 METRIC = "PoseUKF predict+update filter-steps/sec"
 UNIT = "filter-steps/s"
 
@@ -304,7 +308,11 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "pose_fused_kernel<predict, DVL update, 12 warps>",
                              "traffic_source": traffic_src,
-                             "kernel_ms": kern_ms, "alg_bytes_per_filter_step": B_ALG},
+                             "kernel_ms": kern_ms, "alg_bytes_per_filter_step": B_ALG,
+                             "fp64": {"executed_tflops": W_EXEC * B / (kern_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK / 1e12,
+                                      "frac_executed": W_EXEC * B / (kern_ms * 1e-3) / FP64_PEAK,
+                                      "frac_if_reference_flops": W_ALG * B / (kern_ms * 1e-3) / FP64_PEAK,
+                                      "note": "secondary roof; executed flop from the committed ncu capture, peak measured"}},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * 8, "d2h_bytes_per_step": B * 10 * 8,
                         "ms_per_step": e2e_ms / K,
                         "what": "per step: pinned-host gyro+DVL -> HBM, fused step through the C ABI, navigation solution (p,q,v) of every "
