@@ -182,8 +182,6 @@ def main():
             z[o:o + c] = torch.from_numpy(inp["dvl"])
         host_in.append((g, z))
         dev_in.append((g.to(dev), z.to(dev)))
-    nav_host = torch.empty((B, 10), dtype=torch.float64).pin_memory()
-    nav_dev = torch.empty((B, 10), dtype=torch.float64, device=dev)
     torch.cuda.synchronize(dev)
 
     def barrier():
