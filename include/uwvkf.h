@@ -261,6 +261,10 @@ enum uwvkf_debug_what {
   UWVKF_DEBUG_WARP_SUM = 4
 };
 int uwvkf_debug_eval(uwvkf_handle h, int what, const double *in, double *out, int n);
+/* Per-phase latency table of the fused PoseUKF kernel (40 counters: clock cycles summed over the filters of warp 0 of every
+ * CTA, [39] = number of such filters).  Only a library built with -DUWVKF_PHASE_TIMING (tools/phase_timing.py) fills it; the
+ * product build returns UWVKF_ERR_INVALID_ARGUMENT.  No reference counterpart: profiling aid. */
+int uwvkf_debug_phase_cycles(uwvkf_handle h, uint64_t *out, int reset);
 
 /* ---- ensemble statistics (north_star: the only cross-GPU exchange) -------------------------------- */
 /* Writes [count, sum mu (DIM), sum mu mu^T lower triangle row-major (DIM*(DIM+1)/2)] over this handle's filters into

@@ -89,20 +89,45 @@ struct FusedCfg {
   static constexpr int O_L = O_S + PANEL_E;
   static constexpr int O_INVD = O_L + LSZ;
   static constexpr int O_G = O_INVD + KE;          // 3 x KE
-  static constexpr int O_KK = O_G + 3 * KE;        // K rows,      SoA [3][56]
-  static constexpr int O_KS = O_KK + 3 * 56;       // (K S) rows,  SoA [3][56]
-  static constexpr int O_LT = O_KS + 3 * 56;           // rows T of the panel factor, NT x KE
+  static constexpr int O_KC = O_G + 3 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
+                                                   // 128-bit loads hand a whole warp everything column b contributes)
+  static constexpr int O_LT = O_KC + 4 * 54;           // rows T of the panel factor, NT x KE
   static constexpr int TOTAL = O_LT + NT * KE;
-  // per-CTA shared region (doubles): dt^2 Q packed and the products f_a f_b per packed entry (predict only), the entry ->
-  // (row, column) table as byte offsets into the row tables (u32), parameter tables
+  // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
-  static constexpr int C_FF = HAS_PREDICT ? 1432 : 0;
-  static constexpr int C_LUT = C_FF + (HAS_PREDICT ? 1432 : 0);
-  static constexpr int C_FTAB = C_LUT + 716;       // affine factor per tangent index
+  static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
   static constexpr int C_MTAU = C_FTAB + 56;       // -1/tau per stored index (0: not a Gauss-Markov state)
   static constexpr int C_OTAB = C_MTAU + 56;       // shared Markov offsets per stored index (bias offsets)
   static constexpr int CTA = C_OTAB + 56;
 };
+
+// Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
+// clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
+#ifdef UWVKF_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[40];
+#define PH_DECL long long ph_t = clock64();
+#define PH(i) do { __syncwarp(); const long long t_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_ - ph_t)); ph_t = t_; } while (0)
+#define PH_PARAM , long long &ph_t, int phb
+#define PH_ARG(b) , ph_t, b
+#define PHB(i) PH(phb + (i))
+#else
+#define PH_DECL
+#define PH(i)
+#define PH_PARAM
+#define PH_ARG(b)
+#define PHB(i)
+#endif
+
+// st.global.cs under a predicate the compiler cannot turn into a branch around the code that produces the value
+__device__ __forceinline__ void stcs_if(bool p, double *ptr, double v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.cs.f64 [%0], %1;\n\t}" ::"l"(ptr), "d"(v), "r"((unsigned)p) : "memory");
+}
+
+__device__ __forceinline__ double ldcs_v(const double *ptr) {   // ld.global.cs whose issue order the compiler must keep
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(ptr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -261,12 +286,13 @@ __device__ __forceinline__ void g_times_sigma_reg(const double *G, const double 
 // Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh); T stays in registers.
 template <int K, int KE>
 __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double *Lw, const double *invd, double *G, const Quat &qp,
-                                                  int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status) {
+                                                  int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status PH_PARAM) {
   const bool act = p < 2 * K + 1;
   const bool on = act && p > 0;
   const int j = (p - 1) >> 1;
   const double wa = p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
   Quat r = so3_mean_lane(qp, wa, P.mean_tol, P.mean_max_it, status);
+  PHB(0);
   Vec3 a = so3_boxminus(qp, r);
   const double hw = 0.5 * wa;
   soo[0] = wsum(hw * a.x * a.x);
@@ -282,8 +308,11 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
     G[2 * KE + j] = 0.5 * (a.z - nz);
   }
   __syncwarp();
+  PHB(1);
   solve_right_rows<K, 3>(G, KE, Lw, invd, lane);
+  PHB(2);
   g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
+  PHB(3);
   return r;
 }
 
@@ -326,6 +355,80 @@ struct RowData {
   double kk[2][3];   // K rows
 };
 
+// Trailing triangle (columns >= KP of the packed covariance, a contiguous suffix of the filter block), streamed HBM -> registers
+// -> HBM once:   s <- f_a f_b s + dt^2 Q_ab - sum_c (K S)_ac K_bc.
+// Rows keep the owner they have everywhere else in the kernel (x0 = lane, x1 = lane + 32), so the row factors f_a, (K S)_a live in
+// REGISTERS; column b contributes {K_b, f_b} through two broadcast 128-bit shared loads, and the rows b..52 of a column are one
+// contiguous run in memory.  The old values come from the shared-memory staging buffer sS (same indexing as gS) that cp.async
+// filled while the panel work ran, so no global-memory latency is left on this path; the new values go straight to HBM.  A column needs one warp-wide access: the "primary" row of a lane is x1 on lanes 0..20 (rows 32..52) and
+// x0 on lanes 21..31 (rows 21..31); columns b <= 20 need a second, short access for the rows b..20 ("secondary" row x0 of lanes
+// <= 20).  No entry -> (row, column) table, no gathers, no dependent address arithmetic: every column is independent of every
+// other, so the loads of a whole batch of columns are in flight before the first is consumed.
+template <bool AP, bool AK, int KP, int M>
+__device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const double *Qs, const double *KC, const double (&f)[2],
+                                              const double (&ks)[2][3], double q2add, int lane) {
+  const bool lo = lane <= 20;
+  const int rP = lo ? lane + 32 : lane;
+  const double fP = lo ? f[1] : f[0];
+  const double kP0 = lo ? ks[1][0] : ks[0][0], kP1 = lo ? ks[1][1] : ks[0][1], kP2 = lo ? ks[1][2] : ks[0][2];
+  auto entry = [&](int b, int row, double sv, double fr, double k0, double k1, double k2) {
+    const double2 c01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
+    const double2 c2f = *reinterpret_cast<const double2 *>(KC + 4 * b + 2);
+    if (AP) {
+      sv = fma(fr * c2f.y, sv, Qs[coloff(b) + row]);
+      if (b >= T_WV && b < T_BADCP && row == b) sv += q2add;
+    }
+    if (AK) {
+      sv = fma(-k0, c01.x, sv);
+      if (M > 1) sv = fma(-k1, c01.y, sv);
+      if (M > 2) sv = fma(-k2, c2f.x, sv);
+    }
+    return sv;
+  };
+  // Inactive lanes (rows above the diagonal of column b) read the diagonal entry instead and their store is predicated off, so
+  // neither loads nor arithmetic sit behind a branch.  Loads and stores are volatile asm: their program order is the issue order,
+  // which lets the loop below keep the loads of batch i + 1 in flight while batch i is computed and stored (software pipeline;
+  // the triangle was pulled into L2 at the top of the filter's iteration).
+  constexpr int UB = 6, NB = (N - KP + UB - 1) / UB;
+  constexpr int NS = KP <= 20 ? 21 - KP : 0;   // columns that also have secondary rows (b .. 20 on lanes <= 20)
+  double vS[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lo && lane >= KP + u) ? lane : KP + u));
+  double v[2][UB];
+  auto load = [&](int i, double (&dst)[UB]) {
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = KP + i * UB + u;
+      if (b < N) dst[u] = ldcs_v(gS + coloff(b) + (rP >= b ? rP : b));
+    }
+  };
+  auto finish = [&](int i, const double (&src)[UB]) {
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = KP + i * UB + u;
+      if (b < N) {
+        const int rowP = rP >= b ? rP : b;
+        stcs_if(rP >= b, gS + coloff(b) + rowP, entry(b, rowP, src[u], fP, kP0, kP1, kP2));
+      }
+    }
+  };
+  load(0, v[0]);
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (i + 1 < NB) load(i + 1, v[(i + 1) & 1]);
+    if (i == 0) {
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int b = KP + u;
+        const bool actS = lo && lane >= b;
+        const int rowS = actS ? lane : b;
+        stcs_if(actS, gS + coloff(b) + rowS, entry(b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2]));
+      }
+    }
+    finish(i, v[i & 1]);
+  }
+}
+
 // -1/tau of stored component s (0 when the process model leaves it alone), reference src/PoseUKF.cpp:37-78
 __device__ inline double markov_rate(int s, const Params &P) {
   if (s < P_BG) return 0.0;
@@ -342,19 +445,17 @@ __device__ inline double markov_rate(int s, const Params &P) {
 
 // ---------------------------------------------------------------------------------------------------------
 template <int HAS_PREDICT, int KIND, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P, const uint16_t *__restrict__ lut_g) {
+__global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
   using C = FusedCfg<HAS_PREDICT, KIND>;
   constexpr int KP = C::KP, KE = C::KE;
   extern __shared__ __align__(16) double smem[];
   double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
-  double *FF = smem + C::C_FF;                       // f_a f_b per packed entry (only when HAS_PREDICT)
-  const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + C::C_LUT);   // (8 row) | (8 col) << 16
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G;
-  double *KK = w + C::O_KK, *KSs = w + C::O_KS, *LTs = w + C::O_LT;
-  (void)LTs; (void)FF;
+  double *KC = w + C::O_KC, *LTs = w + C::O_LT;
+  (void)LTs;
   {
     const double dt_ = HAS_PREDICT ? a.ops[0].dt : 0.0;
     if (threadIdx.x < 56) {
@@ -363,18 +464,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       mtau[t] = t < DIM ? markov_rate(t, P) : 0.0;
       otab[t] = (t >= P_BG && t < P_BA) ? P.gyro_bias_offset[t - P_BG] : ((t >= P_BA && t < P_G) ? P.acc_bias_offset[t - P_BA] : 0.0);
     }
-    __syncthreads();
-    uint32_t *lw = reinterpret_cast<uint32_t *>(smem + C::C_LUT);
-    for (int e = threadIdx.x; e < NP; e += blockDim.x) {
-      const unsigned ij = lut_g[e];
-      const unsigned ar = ij & 0xff, bc = ij >> 8;
-      lw[e] = (ar * 8u) | ((bc * 8u) << 16);
-      if (HAS_PREDICT) {
-        Qs[e] = (dt_ * dt_) * a.Q[e];
-        FF[e] = ftab[ar] * ftab[bc];
-      }
+    if (HAS_PREDICT) {
+      for (int e = threadIdx.x; e < NP; e += blockDim.x) Qs[e] = (dt_ * dt_) * a.Q[e];
     }
     __syncthreads();
+    // per-warp column table {K_b (zero until an update fills it), f_b}
+    for (int b = lane; b < 54; b += 32) {
+      KC[4 * b] = 0.0; KC[4 * b + 1] = 0.0; KC[4 * b + 2] = 0.0; KC[4 * b + 3] = ftab[b];
+    }
+    __syncwarp();
   }
   const Op &op0 = a.ops[0];
   const Op &opu = a.ops[HAS_PREDICT ? 1 : 0];
@@ -383,6 +481,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const int x0 = lane, x1 = lane + 32;
   const int colane = coloff(lane);
   (void)colane;
+  const double frow[2] = {ftab[x0], ftab[x1 < N ? x1 : N]};   // affine process factor of the rows this lane owns (1 without predict)
 
   // [mu 54 | pad 2 | panel] is a prefix of the filter block.  It is copied global -> shared asynchronously (cp.async, 16 B per
   // lane and step, no registers) ONE FILTER AHEAD: the copies for the warp's next filter are issued as soon as the current
@@ -403,6 +502,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
+    PH_DECL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
@@ -431,12 +531,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     unsigned st = 0;
     bool predicted = false, updated = false;
     double add = 0.0;
+    double ksr[2][3] = {{0, 0, 0}, {0, 0, 0}};   // (K S) rows of the accepted update for the rows this lane owns
 
     // =================================== predict (k = 15) ====================================================
     if constexpr (HAS_PREDICT) {
       constexpr int K = 15;
       const double *wm_g = a.rot_rate + f * 3;
-      if (chol_sq<K>(S, Lw, invd, lane)) {
+      PH(0);
+      const bool spd15 = chol_sq<K>(S, Lw, invd, lane);
+      PH(1);
+      if (spd15) {
         const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
         const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};
         const int p = lane;
@@ -456,8 +560,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           wn.z -= kEarthW * sl;
           qp = so3_boxplus(qq, wn, dt);
         }
+        PH(2);
         double soo[6], T[2][3];
-        Quat r = ori_transform_reg<K, KE>(S, Lw, invd, G, qp, p, P, soo, T, lane, st);
+        Quat r = ori_transform_reg<K, KE>(S, Lw, invd, G, qp, p, P, soo, T, lane, st PH_ARG(3));
         // effective process noise pieces (reference src/PoseUKF.cpp:448-460)
         double qoo[6];
         {
@@ -475,7 +580,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
         }
         add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
-        const double rdf[2] = {ftab[x0], ftab[x1 < N ? x1 : N]};
+        const double (&rdf)[2] = frow;
         // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
         auto new_mean = [&](int sidx_, double offv) {
           const double xv = mu[sidx_];
@@ -492,9 +597,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (x0 < P_ORI || x0 >= P_VEL) nm0 = new_mean(x0, off0);
         if (x1 < DIM) nm1 = new_mean(x1, off1);
         __syncwarp();
+        PH(7);
         // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
         couple3_f<T_POS, T_VEL>(S, dt, lane, colane);
         couple3_f<T_VEL, T_ACC>(S, dt, lane, colane);
+        PH(8);
 #pragma unroll
         for (int b = 0; b < KP; ++b) {
           if (b >= 3 && b < 6) continue;
@@ -506,6 +613,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = fma(rdf[h] * fb, S[cb + x], Qs[cb + x]);
           }
         }
+        PH(9);
         // orientation rows/cols: T F^T (+ Q cross terms)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -533,6 +641,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
         predicted = true;
         __syncwarp();
+        PH(10);
       } else {
         st |= ST_NOT_SPD;
       }
@@ -550,7 +659,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         const int e = coloff(tb) + ta;
         double sv = (blk + OFF_S)[e];
         if (HAS_PREDICT && predicted) {
-          sv = fma(FF[HAS_PREDICT ? e : 0], sv, Qs[HAS_PREDICT ? e : 0]);
+          sv = fma(ftab[ta] * ftab[tb], sv, Qs[HAS_PREDICT ? e : 0]);
           if (ta == tb && tb >= T_WV && tb < T_BADCP) sv += dt2 * add;
         }
         return sv;
@@ -579,7 +688,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             z[0] = z[0] + (mu[0] - opu.aux[0]); z[1] = z[1] + (mu[1] - opu.aux[1]);
           }
         }
+        PH(11);
         if (!chol_sq<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
+        PH(12);
       }
       if (go) {
         double lt[NT > 0 ? NT : 1];   // lane j < K: L[T0 + r][j], rows T of the panel factor Sigma[:, :K] L11^-T
@@ -616,6 +727,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           MM::eval(mu, d, opu.aux, P, Z[r]);
           wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
         }
+        PH(13);
         double zb[M];
 #pragma unroll
         for (int k = 0; k < M; ++k) zb[k] = bcast(Z[0][k], 0);
@@ -636,6 +748,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           } while (nrm > P.mean_tol * P.mean_tol && ++it < P.mean_max_it);   // nrm holds the squared norm
           if (it >= P.mean_max_it) st |= ST_MEAN_NOT_CONVERGED;
         }
+        PH(14);
         double Szz[M * M];
 #pragma unroll
         for (int i = 0; i < M; ++i)
@@ -698,9 +811,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
           __syncwarp();
         }
+        PH(15);
         solve_right_rows<K, M>(G, KE, Lw, invd, lane);
+        PH(16);
         double T[2][M];
         g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
+        PH(17);
         if constexpr (NT > 0) {   // + C Sigma[T, x]: panel columns from shared memory, the rest from the trailing triangle
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -732,7 +848,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         } else {
           // gain rows, (K S) rows and delta for the rows this lane owns; K and K S go straight to the row tables the
           // trailing pass reads (and are re-read from there in the rare rollback) so that they do not stay in registers
-          double dl[2], kk[2][3] = {{0, 0, 0}, {0, 0, 0}}, ks[2][3] = {{0, 0, 0}, {0, 0, 0}};
+          double dl[2], kk[2][3] = {{0, 0, 0}, {0, 0, 0}};
+          double (&ks)[2][3] = ksr;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             double dx = 0;
@@ -753,21 +870,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             }
             dl[h] = dx;
           }
-          // column-side broadcast copy of K
+          // column-side broadcast copy of K (the f_b slot of the table is never rewritten)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
             if (x < N) {
-              KK[x] = kk[h][0]; KK[56 + x] = kk[h][1]; KK[112 + x] = kk[h][2];
-              KSs[x] = ks[h][0]; KSs[56 + x] = ks[h][1]; KSs[112 + x] = ks[h][2];
+              *reinterpret_cast<double2 *>(KC + 4 * x) = make_double2(kk[h][0], kk[h][1]);
+              KC[4 * x + 2] = kk[h][2];
             }
           }
           __syncwarp();
+          PH(18);
           // panel downdate: Sigma[x][b] -= (KS)_x . K_b
 #pragma unroll
           for (int b = 0; b < KP; ++b) {
             const int cb = coloff(b);
-            const double k0 = KK[b], k1 = KK[56 + b], k2 = KK[112 + b];
+            const double2 k01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
+            const double k0 = k01.x, k1 = k01.y, k2 = KC[4 * b + 2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
@@ -781,9 +900,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             }
           }
           __syncwarp();
+          PH(19);
           // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
           constexpr int KA = 6;
-          if (chol_sq<KA>(S, Lw, invd, lane)) {
+          const bool spd6 = chol_sq<KA>(S, Lw, invd, lane);
+          PH(20);
+          if (spd6) {
             const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
             const double d3 = bcast(dl[0], 3), d4 = bcast(dl[0], 4), d5 = bcast(dl[0], 5);
             const int p = lane;
@@ -792,8 +914,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             const double sg = (p & 1) ? 1.0 : -1.0;
             auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<KA> + t] : 0.0; };
             Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
+            PH(21);
             double soo[6], TA[2][3];
-            Quat r = ori_transform_reg<KA, KE>(S, Lw, invd, G, qp, p, P, soo, TA, lane, st);
+            Quat r = ori_transform_reg<KA, KE>(S, Lw, invd, G, qp, p, P, soo, TA, lane, st PH_ARG(22));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
@@ -814,21 +937,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
             updated = true;
             __syncwarp();
+            PH(26);
           } else {
             // the downdated covariance lost definiteness in its leading block: roll the panel back, drop the update
             st |= ST_NOT_SPD;
 #pragma unroll 1
             for (int b = 0; b < KP; ++b) {
               const int cb = coloff(b);
-              const double k0 = KK[b], k1 = KK[56 + b], k2 = KK[112 + b];
+              const double k0 = KC[4 * b], k1 = KC[4 * b + 1], k2 = KC[4 * b + 2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int x = lane + 32 * h;
                 if (x >= b && x < N) {
                   double s = S[cb + x];
-                  s = fma(KSs[x], k0, s);
-                  if (M > 1) s = fma(KSs[56 + x], k1, s);
-                  if (M > 2) s = fma(KSs[112 + x], k2, s);
+                  s = fma(ksr[h][0], k0, s);
+                  if (M > 1) s = fma(ksr[h][1], k1, s);
+                  if (M > 2) s = fma(ksr[h][2], k2, s);
                   S[cb + x] = s;
                 }
               }
@@ -837,19 +961,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
         }
       }
-      if (!updated && predicted) {   // the trailing pass below then applies the process map only: K = K S = 0
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int x = lane + 32 * h;
-          if (x < N) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { KK[56 * c + x] = 0.0; KSs[56 * c + x] = 0.0; }
-          }
-        }
-      }
     }
 
     // =================================== write back ===========================================================
+    PH(27);
     if (predicted || updated) {
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
@@ -864,51 +979,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         const long long fn = f + (long long)gridDim.x * WARPS;
         if (fn < a.B) fetch_prefix(fn);
       }
-      // trailing triangle (columns >= KP): a contiguous suffix of the packed array, streamed HBM -> registers -> HBM in flat
-      // order (fully coalesced):  s <- (f_a f_b) s + dt^2 Q_ab - sum_c (K S)_ac K_bc.  f_a f_b and dt^2 Q come from per-CTA
-      // tables indexed like the entry, the row/column offsets into the K tables from the LUT; the four water-velocity diagonal
-      // entries that also receive the velocity-dependent noise sit at compile-time (round, lane) positions.
+      // trailing triangle (columns >= KP), see trailing_pass: process map and / or rank-M downdate, whichever happened
+      PH(28);
       double *gS = blk + OFF_S;
-      constexpr int NTR = NP - C::PANEL, ROUNDS_T = (NTR + 31) / 32, UB = 8;
       const double q2add = dt2 * add;
-      auto pass = [&](auto apply_predict) {
-        constexpr bool AP = decltype(apply_predict)::value;
-#pragma unroll 1   // kept rolled: the kernel's hot code is ~80 KB of straight-line SASS and instruction fetch shows up in ncu
-        for (int t0 = 0; t0 < ROUNDS_T; t0 += UB) {
-          double v[UB];
-#pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const int t = t0 + u, e = C::PANEL + lane + 32 * t;
-            if (t < ROUNDS_T) v[u] = (t < ROUNDS_T - 1 || e < NP) ? __ldcs(gS + e) : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const int t = t0 + u, e = C::PANEL + lane + 32 * t;
-            if (t < ROUNDS_T && (t < ROUNDS_T - 1 || e < NP)) {
-              double sv = v[u];
-              if (AP) {
-                sv = fma(FF[e], sv, Qs[e]);
-#pragma unroll
-                for (int dg = T_WV; dg < T_BADCP; ++dg) {
-                  const int ed = cidx(dg, dg) - C::PANEL;
-                  if (t == ed / 32 && lane == ed % 32) sv += q2add;
-                }
-              }
-              if (KIND != M_NONE) {
-                const unsigned ij = lut[e];
-                const char *kr = reinterpret_cast<const char *>(KSs) + (ij & 0xffffu);
-                const char *kc = reinterpret_cast<const char *>(KK) + (ij >> 16);
-                sv = fma(-*reinterpret_cast<const double *>(kr), *reinterpret_cast<const double *>(kc), sv);
-                sv = fma(-*reinterpret_cast<const double *>(kr + 448), *reinterpret_cast<const double *>(kc + 448), sv);
-                sv = fma(-*reinterpret_cast<const double *>(kr + 896), *reinterpret_cast<const double *>(kc + 896), sv);
-              }
-              __stcs(gS + e, sv);
-            }
-          }
-        }
-      };
-      if (HAS_PREDICT && predicted) pass(std::true_type{});
-      else pass(std::false_type{});
+      constexpr int MM_ = (KIND == M_NONE) ? 1 : C::MF::M;
+      if constexpr (KIND == M_NONE) {
+        trailing_pass<true, false, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+      } else if constexpr (!HAS_PREDICT) {
+        trailing_pass<false, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+      } else {
+        if (predicted && updated) trailing_pass<true, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+        else if (predicted) trailing_pass<true, false, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+        else trailing_pass<false, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+      }
     }
     else {
       __syncwarp();
@@ -917,6 +1001,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     }
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();
+    PH(29);
+#ifdef UWVKF_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[39], 1ull);
+#endif
   }
 }
 

@@ -342,15 +342,13 @@ int launch_fused(uwvkf_handle h, const pose::Launch &L) {
   constexpr int WARPS = fused_warps<HP, KIND>();
   size_t smem = (size_t)(C::CTA + WARPS * C::TOTAL) * sizeof(double);
   static unsigned long long attr_set = 0;   // one bit per device
-  uint16_t *lut_dev = nullptr;
-  CK(cudaGetSymbolAddress((void **)&lut_dev, g_lut));
   if (!(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << h->device;
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
-  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp, lut_dev);
+  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
   CK(cudaGetLastError());
   h->launches++;
   return UWVKF_OK;
@@ -991,6 +989,24 @@ int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose7) {
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   return UWVKF_OK;
+}
+
+int uwvkf_debug_phase_cycles(uwvkf_handle h, uint64_t *out, int reset) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (!out) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null output");
+  CK(cudaStreamSynchronize(h->stream));
+#ifdef UWVKF_PHASE_TIMING
+  CK(cudaMemcpyFromSymbol(out, pose::g_phase_cycles, 40 * sizeof(uint64_t)));
+  if (reset) {
+    static const uint64_t zeros[40] = {0};
+    CK(cudaMemcpyToSymbol(pose::g_phase_cycles, zeros, sizeof(zeros)));
+  }
+  return UWVKF_OK;
+#else
+  (void)reset;
+  for (int i = 0; i < 40; ++i) out[i] = 0;
+  return fail(UWVKF_ERR_INVALID_ARGUMENT, "library was built without -DUWVKF_PHASE_TIMING");
+#endif
 }
 
 int uwvkf_debug_eval(uwvkf_handle h, int what, const double *in, double *out, int n) {
