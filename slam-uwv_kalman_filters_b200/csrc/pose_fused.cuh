@@ -87,9 +87,8 @@ struct FusedCfg {
   static constexpr int O_MU = 0;                   // 56
   static constexpr int O_S = 56;                   // panel (same indexing as the full packed array)
   static constexpr int O_L = O_S + PANEL_E;
-  static constexpr int O_INVD = O_L + LSZ;
-  static constexpr int O_G = O_INVD + KE;          // 3 x KE
-  static constexpr int O_KC = O_G + 3 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
+  static constexpr int O_G = O_L + LSZ;          // per sigma-point pair j: {A[0][j], A[1][j], A[2][j], -}, AoS [KE][4]
+  static constexpr int O_KC = O_G + 4 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
                                                    // 128-bit loads hand a whole warp everything column b contributes)
   static constexpr int O_LT = O_KC + 4 * 54;           // rows T of the panel factor, NT x KE
   static constexpr int TOTAL = O_LT + NT * KE;
@@ -154,19 +153,21 @@ __device__ __forceinline__ double wsum(double v) {
 // "lane = row" and for "lane = column" accesses): L[i][j] = Lw[j * LStride<K> + i].
 template <int K> constexpr int LStride = K | 1;
 
-// Right-looking Cholesky of the leading K x K block (K <= 32): lane i owns row i in registers; the finished column j goes
-// to shared memory (it is needed there anyway) and the other lanes read L[c][j] back as broadcast loads instead of one
-// shuffle pair per entry.  Entries above the diagonal and lanes >= K carry don't-care values that are never consumed.
+// Cholesky of the leading K x K block carried over the WHOLE panel: besides the factor L11 (to shared memory, for the sigma
+// points) every lane ends up with the rows x0 = lane and x1 = lane + 32 of the panel factor Lp = Sigma[:, :K] L11^-T in registers.
+// The rows below the block ride along in the rank-1 updates (lanes >= K were idle in them anyway; the x1 rows cost K(K+1)/2 more
+// DFMA), and they replace both the triangular solve G = A L11^-1 and the product G Sigma[:K, :] of the unscented transform:
+//   A L11^-1 Sigma[:K, x] = A (Lp[x, :])^T                       (Sigma[:K, x] = L11 Lp[x, :]^T),
+// i.e. cross-covariances become K-term dot products of registers with broadcast rows of A: no solve, no re-read of Sigma.
 template <int K>
-__device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *invd, int lane) {
+__device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane, double (&a0)[K], double (&a1)[K]) {
   static_assert(K <= 32, "one row per lane");
   constexpr int LS = LStride<K>;
-  double a[K];
+  const int x1 = lane + 32 < N ? lane + 32 : lane;   // lanes without a second row duplicate the first (never consumed)
 #pragma unroll
-  for (int c = 0; c < K; ++c) a[c] = S[coloff(c) + lane];
-  // the pivots are the critical path (broadcast -> rsqrt -> scale, K times).  Lane i's diagonal entry only ever receives
-  // -L[i][j]^2, products of the lane's OWN column entries, so it is tracked in a register of its own: the next pivot never
-  // waits for the shared-memory round trip that carries the finished column to the other lanes.
+  for (int c = 0; c < K; ++c) { a0[c] = S[coloff(c) + lane]; a1[c] = S[coloff(c) + x1]; }
+  // pivots: lane i's diagonal entry only ever receives -L[i][j]^2, products of the lane's own entries, so it is tracked in a
+  // register of its own and never waits for the shared-memory round trip that carries the finished column to the other lanes
   double dg = S[cidx(lane < K ? lane : 0, lane < K ? lane : 0)];
   bool ok = true;
 #pragma unroll
@@ -174,73 +175,49 @@ __device__ __forceinline__ bool chol_sq(const double *S, double *Lw, double *inv
     const double d = bcast(dg, j);
     ok = ok && (d > 0.0);
     const double inv = fast_rsqrt3(d);
-    a[j] *= inv;                          // lane j: d / sqrt(d) = L[j][j]; lanes > j: L[i][j]
-    dg = fma(-a[j], a[j], dg);            // lanes > j (don't care elsewhere)
-    if (lane < K) Lw[j * LS + lane] = a[j];
-    if (lane == 0) invd[j] = inv;
+    a0[j] *= inv;                           // lane j: d / sqrt(d) = L[j][j]; other rows: L[i][j]
+    a1[j] *= inv;
+    dg = fma(-a0[j], a0[j], dg);
+    if (lane < K) Lw[j * LS + lane] = a0[j];
     __syncwarp();
-    // column j of L back as broadcast loads, two entries per 128-bit load where the (compile-time) offset is 16-byte aligned
-    // (Lw itself is 16-byte aligned: every region of the per-warp layout starts at an even double offset)
     {
       int c = j + 1;
-      if (((j * LS + c) & 1) && c < K) { a[c] = fma(-a[j], Lw[j * LS + c], a[c]); ++c; }
+      if (((j * LS + c) & 1) && c < K) {
+        const double l = Lw[j * LS + c];
+        a0[c] = fma(-a0[j], l, a0[c]); a1[c] = fma(-a1[j], l, a1[c]); ++c;
+      }
 #pragma unroll
       for (; c + 1 < K; c += 2) {
         const double2 l2 = *reinterpret_cast<const double2 *>(Lw + j * LS + c);
-        a[c] = fma(-a[j], l2.x, a[c]);
-        a[c + 1] = fma(-a[j], l2.y, a[c + 1]);
+        a0[c] = fma(-a0[j], l2.x, a0[c]); a1[c] = fma(-a1[j], l2.x, a1[c]);
+        a0[c + 1] = fma(-a0[j], l2.y, a0[c + 1]); a1[c + 1] = fma(-a1[j], l2.y, a1[c + 1]);
       }
-      if (c < K) a[c] = fma(-a[j], Lw[j * LS + c], a[c]);
+      if (c < K) {
+        const double l = Lw[j * LS + c];
+        a0[c] = fma(-a0[j], l, a0[c]); a1[c] = fma(-a1[j], l, a1[c]);
+      }
     }
   }
+  // rows inside the block: the entries above the diagonal are zeros of L11 (the loop carried don't-care values there)
+#pragma unroll
+  for (int j = 1; j < K; ++j) a0[j] = (j > lane) ? 0.0 : a0[j];
   return ok;
 }
 
-// G <- G L^-1 with one LANE PER ROW of G (M <= 3 lanes busy) and the whole row in registers: the dependent chain per column
-// is one DMUL + one DFMA instead of a shuffle pair + DMUL + DFMA, and nothing goes through the shuffle network.  Entries of L
-// come in as broadcast loads.  The kernel is bound by dependent-issue latency, so the idle lanes cost nothing.
+// T[h][c] = sum_j A[c][j] Lp[x_h][j]: rows of the panel factor from registers, A (M x K, stored [j][4]) as broadcast loads
 template <int K, int M>
-__device__ __forceinline__ void solve_right_rows(double *G, int gs, const double *Lw, const double *invd, int lane) {
-  constexpr int LS = LStride<K>;
-  const int r = lane < M ? lane : 0;
-  double x[K];
+__device__ __forceinline__ void a_times_panel(const double *G, const double (&a0)[K], const double (&a1)[K], double (&T)[2][M]) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) x[k] = G[r * gs + k];
+  for (int c = 0; c < M; ++c) { T[0][c] = 0.0; T[1][c] = 0.0; }
 #pragma unroll
-  for (int c = K - 1; c >= 0; --c) {
-    x[c] *= invd[c];
+  for (int j = 0; j < K; ++j) {
+    double aj[3];
+    const double2 g01 = *reinterpret_cast<const double2 *>(G + 4 * j);
+    aj[0] = g01.x; aj[1] = g01.y; aj[2] = 0.0;
+    if (M > 2) aj[2] = G[4 * j + 2];
 #pragma unroll
-    for (int k = c - 1; k >= 0; --k) x[k] = fma(-x[c], Lw[k * LS + c], x[k]);
+    for (int c = 0; c < M; ++c) { T[0][c] = fma(aj[c], a0[j], T[0][c]); T[1][c] = fma(aj[c], a1[j], T[1][c]); }
   }
-  if (lane < M) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) G[r * gs + k] = x[k];
-  }
-  __syncwarp();
-}
-
-// G <- G L^-1 (G is M x K, row stride gs; lane = column).  Column c is final once steps K-1..c+1 have been applied; its
-// scaling by 1/L[c][c] is folded into the broadcast value, and lane c scales its own entry after the loop, so the loop body
-// has no per-lane special case: M x (DMUL + shuffle pair + DFMA) and one predicated load per column.
-template <int K, int M>
-__device__ __forceinline__ void solve_right_sq(double *G, int gs, const double *Lw, const double *invd, int lane) {
-  constexpr int LS = LStride<K>;
-  double acc[M];
-#pragma unroll
-  for (int r = 0; r < M; ++r) acc[r] = (lane < K) ? G[r * gs + lane] : 0.0;
-#pragma unroll
-  for (int c = K - 1; c > 0; --c) {
-    const double ic = invd[c];
-    const double l = (lane < c) ? Lw[lane * LS + c] : 0.0;
-#pragma unroll
-    for (int r = 0; r < M; ++r) acc[r] = fma(-(bcast(acc[r], c) * ic), l, acc[r]);
-  }
-  if (lane < K) {
-    const double il = invd[lane];
-#pragma unroll
-    for (int r = 0; r < M; ++r) G[r * gs + lane] = acc[r] * il;
-  }
-  __syncwarp();
 }
 
 // equal-weight iterated SO3 mean over 2N+1 logical points, one point (with multiplicity wt) per lane
@@ -262,30 +239,9 @@ __device__ __forceinline__ Quat so3_mean_lane(const Quat &qp, double wt, double 
   return r;
 }
 
-// T[c] = sum_{b<K} G[c][b] * Sigma[b][x] for the two rows x0 = lane, x1 = lane + 32 owned by this lane (registers)
-template <int K, int M, int KE>
-__device__ __forceinline__ void g_times_sigma_reg(const double *G, const double *S, int lane, double (&T)[2][M]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int x = lane + 32 * h;
-    const int cox = coloff(x < N ? x : 0);
-#pragma unroll
-    for (int c = 0; c < M; ++c) T[h][c] = 0.0;
-    if (x < N) {
-#pragma unroll
-      for (int b = 0; b < K; ++b) {
-        const int e = (x >= b) ? (coloff(b) + x) : (cox + b);
-        const double s = S[e];
-#pragma unroll
-        for (int c = 0; c < M; ++c) T[h][c] = fma(G[c * KE + b], s, T[h][c]);
-      }
-    }
-  }
-}
-
 // Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh); T stays in registers.
-template <int K, int KE>
-__device__ __forceinline__ Quat ori_transform_reg(const double *S, const double *Lw, const double *invd, double *G, const Quat &qp,
+template <int K>
+__device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[K], const double (&a1)[K], const Quat &qp,
                                                   int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status PH_PARAM) {
   const bool act = p < 2 * K + 1;
   const bool on = act && p > 0;
@@ -303,15 +259,13 @@ __device__ __forceinline__ Quat ori_transform_reg(const double *S, const double 
   soo[5] = wsum(hw * a.z * a.z);
   double nx = __shfl_down_sync(kFull, a.x, 1), ny = __shfl_down_sync(kFull, a.y, 1), nz = __shfl_down_sync(kFull, a.z, 1);
   if (on && (p & 1)) {
-    G[0 * KE + j] = 0.5 * (a.x - nx);
-    G[1 * KE + j] = 0.5 * (a.y - ny);
-    G[2 * KE + j] = 0.5 * (a.z - nz);
+    *reinterpret_cast<double2 *>(G + 4 * j) = make_double2(0.5 * (a.x - nx), 0.5 * (a.y - ny));
+    G[4 * j + 2] = 0.5 * (a.z - nz);
   }
   __syncwarp();
   PHB(1);
-  solve_right_rows<K, 3>(G, KE, Lw, invd, lane);
   PHB(2);
-  g_times_sigma_reg<K, 3, KE>(G, S, lane, T);
+  a_times_panel<K, 3>(G, a0, a1, T);
   PHB(3);
   return r;
 }
@@ -453,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *w = smem + C::CTA + warp * C::TOTAL;
-  double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *invd = w + C::O_INVD, *G = w + C::O_G;
+  double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *G = w + C::O_G;
   double *KC = w + C::O_KC, *LTs = w + C::O_LT;
   (void)LTs;
   {
@@ -538,7 +492,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       constexpr int K = 15;
       const double *wm_g = a.rot_rate + f * 3;
       PH(0);
-      const bool spd15 = chol_sq<K>(S, Lw, invd, lane);
+      double a0[K], a1[K];
+      const bool spd15 = chol_panel<K>(S, Lw, lane, a0, a1);
       PH(1);
       if (spd15) {
         const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
@@ -562,7 +517,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         }
         PH(2);
         double soo[6], T[2][3];
-        Quat r = ori_transform_reg<K, KE>(S, Lw, invd, G, qp, p, P, soo, T, lane, st PH_ARG(3));
+        Quat r = ori_transform_reg<K>(G, a0, a1, qp, p, P, soo, T, lane, st PH_ARG(3));
         // effective process noise pieces (reference src/PoseUKF.cpp:448-460)
         double qoo[6];
         {
@@ -669,6 +624,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       (void)sig;
       bool go = !(opu.valid && !opu.valid[f]);
       double z[M], Rm[M * M];
+      double u0[K], u1[K];   // rows x0, x1 of the panel factor (chol_panel)
       if (go) {
         bool bad = false;
 #pragma unroll
@@ -689,28 +645,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
         }
         PH(11);
-        if (!chol_sq<K>(S, Lw, invd, lane)) { st |= ST_NOT_SPD; go = false; }
+        if (!chol_panel<K>(S, Lw, lane, u0, u1)) { st |= ST_NOT_SPD; go = false; }
         PH(12);
       }
       if (go) {
         double lt[NT > 0 ? NT : 1];   // lane j < K: L[T0 + r][j], rows T of the panel factor Sigma[:, :K] L11^-T
         if constexpr (NT > 0) {
+          // rows T of the panel factor sit in the registers of the lanes that own those rows: transpose through shared memory
 #pragma unroll
-          for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? S[coloff(lane) + MM::tail(r)] : 0.0;
-          for (int k = 0; k < K; ++k) {   // forward substitution, one column of L11 per step
-            const double ik = invd[k];
-            const double l = (lane > k && lane < K) ? Lw[k * LStride<K> + lane] : 0.0;
+          for (int r = 0; r < NT; ++r) {
+            constexpr int dummy = 0; (void)dummy;
+            const int t = MM::tail(r);
+            if (lane == (t & 31)) {
 #pragma unroll
-            for (int r = 0; r < NT; ++r) {
-              const double xk = bcast(lt[r] * ik, k);
-              lt[r] = (lane == k) ? xk : fma(-xk, l, lt[r]);
+              for (int j = 0; j < K; ++j) LTs[r * KE + j] = (t >= 32) ? u1[j] : u0[j];
             }
           }
-          if (lane < K) {
-#pragma unroll
-            for (int r = 0; r < NT; ++r) LTs[r * KE + lane] = lt[r];
-          }
           __syncwarp();
+#pragma unroll
+          for (int r = 0; r < NT; ++r) lt[r] = (lane < K) ? LTs[r * KE + lane] : 0.0;
         }
         double Z[ROUNDS][M], wt[ROUNDS];
 #pragma unroll
@@ -769,7 +722,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             double src = Z[r][k];
             if (r + 1 < ROUNDS) { if (lane == 0) src = Z[r + 1 < ROUNDS ? r + 1 : r][k]; }
             double nxt = __shfl_sync(kFull, src, (lane + 1) & 31);
-            if ((p & 1) && p < NPTS) G[k * KE + ((p - 1) >> 1)] = 0.5 * (Z[r][k] - nxt);
+            if ((p & 1) && p < NPTS) G[4 * ((p - 1) >> 1) + k] = 0.5 * (Z[r][k] - nxt);
           }
         }
         __syncwarp();
@@ -807,15 +760,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             }
           if (lane < K) {
 #pragma unroll
-            for (int c = 0; c < M; ++c) G[c * KE + lane] -= U[c];
+            for (int c = 0; c < M; ++c) G[4 * lane + c] -= U[c];
           }
           __syncwarp();
         }
         PH(15);
-        solve_right_rows<K, M>(G, KE, Lw, invd, lane);
         PH(16);
         double T[2][M];
-        g_times_sigma_reg<K, M, KE>(G, S, lane, T);   // T[h][c] = Pxz[x_h][c]
+        a_times_panel<K, M>(G, u0, u1, T);   // T[h][c] = Pxz[x_h][c] = sum_j B[c][j] Lp[x_h][j]
         PH(17);
         if constexpr (NT > 0) {   // + C Sigma[T, x]: panel columns from shared memory, the rest from the trailing triangle
 #pragma unroll
@@ -903,7 +855,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           PH(19);
           // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
           constexpr int KA = 6;
-          const bool spd6 = chol_sq<KA>(S, Lw, invd, lane);
+          double c0[KA], c1[KA];
+          const bool spd6 = chol_panel<KA>(S, Lw, lane, c0, c1);
           PH(20);
           if (spd6) {
             const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
@@ -916,7 +869,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
             PH(21);
             double soo[6], TA[2][3];
-            Quat r = ori_transform_reg<KA, KE>(S, Lw, invd, G, qp, p, P, soo, TA, lane, st PH_ARG(22));
+            Quat r = ori_transform_reg<KA>(G, c0, c1, qp, p, P, soo, TA, lane, st PH_ARG(22));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
