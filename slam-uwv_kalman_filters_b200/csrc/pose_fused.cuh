@@ -270,36 +270,66 @@ __device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[
   return r;
 }
 
-// In-place congruence Sigma <- C Sigma C^T with C = I + dt E(rows D0.. <- rows S0..) on 3 consecutive rows (same result as
-// couple3 in pose_engine.cuh).  Row / column indices known at compile time give constant column offsets; only the
-// lane-dependent side of an entry needs coloff(lane), which the caller hoists out of the filter loop.
-template <int D0, int S0>
-__device__ __forceinline__ void couple3_f(double *S, double dt, int lane, int colane) {
-  auto pidx = [&](int fixed, int b, int cob) { return (b >= fixed) ? coloff(fixed) + b : cob + fixed; };
-  double nb = 0.0;
-  int eb = 0;
-  if (lane < 6) {
-    const int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
-    const int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-    eb = cidx(D0 + bi, D0 + bj);
-    nb = S[eb] + dt * (S[sidx(S0 + bi, D0 + bj)] + S[sidx(D0 + bi, S0 + bj)]) + dt * dt * S[sidx(S0 + bi, S0 + bj)];
-  }
-  __syncwarp();
+// Panel part of Sigma <- F Sigma F^T + dt^2 Q for the affine rows, F = diag(f) + dt E, E: position <- velocity, velocity <-
+// acceleration (the two couplings commute to first order: E_va E_pv = 0, so F is exactly the product the sequential couple3_f
+// calls apply).  An entry (x, b) reads at most four old entries -- (x, b), (x', b), (x, b'), (x', b') with x' / b' the coupled
+// partner of its row / column -- and partners only point "down" the chain p -> v -> a.  Hence: the three position columns first
+// (new values into registers, one barrier, write), then the three velocity columns the same way, then every other column in
+// place.  Two barriers instead of six and no read-modify-write chains through shared memory.  Orientation rows and columns are
+// left alone (the caller overwrites them with the unscented transform).
+template <int KP>
+__device__ __forceinline__ void process_panel(double *S, const double *Qs, const double *ftab, const double (&f)[2], double dt, int lane,
+                                              int colane) {
+  const double dt2 = dt * dt;
+  const bool rp = lane < 3 || (lane >= T_VEL && lane < T_ACC);   // row x0 = lane has a coupled partner (rows x1 never do)
+  const int px = lane + (lane < 3 ? 6 : 3);
+  const int copx = coloff(px);
+  auto group = [&](auto b0_, auto pbo_) {
+    constexpr int b0 = decltype(b0_)::value, pbo = decltype(pbo_)::value;
+    double nv[3][2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int b = lane + 32 * h;
-    const int cob = h ? coloff(b) : colane;
-    if (b < N && (b < D0 || b >= D0 + 3)) {
+    for (int i = 0; i < 3; ++i) {
+      constexpr int dummy = 0; (void)dummy;
+      const int b = b0 + i, pb = b + pbo, cb = coloff(b), cpb = coloff(pb);
+      const double fb = ftab[b];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int ed = pidx(D0 + i, b, cob), es = pidx(S0 + i, b, cob);
-        S[ed] = fma(dt, S[es], S[ed]);
+      for (int h = 0; h < 2; ++h) {
+        const int x = lane + 32 * h;
+        const int cox = h ? coloff(x < N ? x : 0) : colane;
+        double val = 0.0;
+        if (x >= b && x < N && !(x >= 3 && x < 6)) {
+          val = fma(f[h] * fb, S[cb + x], Qs[cb + x]);
+          val = fma(dt * f[h], S[x >= pb ? cpb + x : cox + pb], val);
+          if (h == 0 && rp) {
+            val = fma(dt * fb, S[cb + px], val);
+            val = fma(dt2, S[px >= pb ? cpb + px : copx + pb], val);
+          }
+        }
+        nv[i][h] = val;
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = b0 + i, x = lane + 32 * h;
+        if (x >= b && x < N && !(x >= 3 && x < 6)) S[coloff(b) + x] = nv[i][h];
+      }
+    __syncwarp();
+  };
+  group(std::integral_constant<int, T_POS>{}, std::integral_constant<int, 6>{});
+  group(std::integral_constant<int, T_VEL>{}, std::integral_constant<int, 3>{});
+#pragma unroll
+  for (int b = T_ACC; b < KP; ++b) {
+    const int cb = coloff(b);
+    const double fb = ftab[b];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x = lane + 32 * h;
+      if (x >= b && x < N) S[cb + x] = fma(f[h] * fb, S[cb + x], Qs[cb + x]);
+    }
   }
-  __syncwarp();
-  if (lane < 6) S[eb] = nb;
-  __syncwarp();
 }
 
 // per-lane row data for the rows x0 = lane and x1 = lane + 32
@@ -553,21 +583,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (x1 < DIM) nm1 = new_mean(x1, off1);
         __syncwarp();
         PH(7);
-        // panel <- F panel F^T : couplings (rows/cols < 12, all inside the panel), then scaling + Q column by column
-        couple3_f<T_POS, T_VEL>(S, dt, lane, colane);
-        couple3_f<T_VEL, T_ACC>(S, dt, lane, colane);
+        // panel <- F panel F^T + dt^2 Q on the affine rows (couplings and scaling in one pass)
         PH(8);
-#pragma unroll
-        for (int b = 0; b < KP; ++b) {
-          if (b >= 3 && b < 6) continue;
-          const int cb = coloff(b);
-          const double fb = ftab[b];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int x = lane + 32 * h;
-            if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = fma(rdf[h] * fb, S[cb + x], Qs[cb + x]);
-          }
-        }
+        process_panel<KP>(S, Qs, ftab, rdf, dt, lane, colane);
         PH(9);
         // orientation rows/cols: T F^T (+ Q cross terms)
 #pragma unroll
