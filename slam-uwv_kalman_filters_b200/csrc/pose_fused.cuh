@@ -102,6 +102,12 @@ struct FusedCfg {
 
 // Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
 // clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
+#ifndef UWVKF_CHOL_SHFL_NEXT
+#define UWVKF_CHOL_SHFL_NEXT 0
+#endif
+#ifndef UWVKF_TRAIL_PREFETCH_L1
+#define UWVKF_TRAIL_PREFETCH_L1 0
+#endif
 #ifdef UWVKF_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[40];
 #define PH_DECL long long ph_t = clock64();
@@ -129,6 +135,7 @@ __device__ __forceinline__ double ldcs_v(const double *ptr) {   // ld.global.cs 
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int coloff(int j) { return j * N - ((j * (j - 1)) >> 1) - j; }   // cidx(i, j) = coloff(j) + i
 
@@ -179,9 +186,20 @@ __device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane
     a1[j] *= inv;
     dg = fma(-a0[j], a0[j], dg);
     if (lane < K) Lw[j * LS + lane] = a0[j];
+#if UWVKF_CHOL_SHFL_NEXT
+    // the next column is the only one the critical path needs at once: its multiplier L[j+1][j] comes by shuffle, the
+    // columns behind it through shared memory as before
+    if (j + 1 < K) {
+      const double ln = bcast(a0[j], j + 1);
+      a0[j + 1] = fma(-a0[j], ln, a0[j + 1]); a1[j + 1] = fma(-a1[j], ln, a1[j + 1]);
+    }
+    constexpr int CN = 2;
+#else
+    constexpr int CN = 1;
+#endif
     __syncwarp();
     {
-      int c = j + 1;
+      int c = j + CN;
       if (((j * LS + c) & 1) && c < K) {
         const double l = Lw[j * LS + c];
         a0[c] = fma(-a0[j], l, a0[c]); a1[c] = fma(-a1[j], l, a1[c]); ++c;
@@ -236,6 +254,15 @@ __device__ __forceinline__ Quat so3_mean_lane(const Quat &qp, double wt, double 
     nrm2 = mx * mx + my * my + mz * mz;
   } while (nrm2 > tol2 && ++it < max_it);
   if (it >= max_it) status |= ST_MEAN_NOT_CONVERGED;
+  return r;
+}
+
+// v[i] for a lane-dependent i without turning v into a local-memory array (shared memory takes most of the L1 here, so
+// local-memory traffic is served at L2 latency)
+__device__ __forceinline__ double pick6(const double (&v)[6], int i) {
+  double r = v[0];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) r = (i == k) ? v[k] : r;
   return r;
 }
 
@@ -494,7 +521,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     {
       const char *tr = reinterpret_cast<const char *>(blk + OFF_S + C::PANEL);
       constexpr int TB = (NP - C::PANEL) * 8;
+#if UWVKF_TRAIL_PREFETCH_L1
+      for (int o = lane * 128; o < TB; o += 32 * 128) prefetch_l1(tr + o);
+#else
       for (int o = lane * 128; o < TB; o += 32 * 128) prefetch_l2(tr + o);
+#endif
       const long long fn = f + (long long)gridDim.x * WARPS;
       if (fn < a.B) {
         const char *nx = reinterpret_cast<const char *>(a.state + fn * BLK);
@@ -607,7 +638,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (lane < 6) {
           int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
           int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-          S[cidx(3 + bi, 3 + bj)] = soo[lane] + qoo[lane];
+          S[cidx(3 + bi, 3 + bj)] = pick6(soo, lane) + pick6(qoo, lane);
         }
         if (x0 < P_ORI || x0 >= P_VEL) mu[x0] = nm0;
         if (x1 < DIM) mu[x1] = nm1;
@@ -899,7 +930,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (lane < 6) {
               int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
               int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-              S[cidx(3 + bi, 3 + bj)] = soo[lane];
+              S[cidx(3 + bi, 3 + bj)] = pick6(soo, lane);
             }
             // mu (+)= delta on the vector components: tangent x -> stored x (x < 3) or x + 1 (x >= 6)
             if (x0 < 3) mu[x0] += dl[0];
