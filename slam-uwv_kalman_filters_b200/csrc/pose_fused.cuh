@@ -91,7 +91,8 @@ struct FusedCfg {
   static constexpr int O_KC = O_G + 4 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
                                                    // 128-bit loads hand a whole warp everything column b contributes)
   static constexpr int O_LT = O_KC + 4 * 54;           // rows T of the panel factor, NT x KE
-  static constexpr int TOTAL = O_LT + NT * KE;
+  static constexpr int O_IN = O_LT + NT * KE;          // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M)
+  static constexpr int TOTAL = O_IN + 8;
   // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
@@ -102,9 +103,6 @@ struct FusedCfg {
 
 // Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
 // clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
-#ifndef UWVKF_CHOL_SHFL_NEXT
-#define UWVKF_CHOL_SHFL_NEXT 0
-#endif
 #ifndef UWVKF_TRAIL_PREFETCH_L1
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
@@ -186,20 +184,9 @@ __device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane
     a1[j] *= inv;
     dg = fma(-a0[j], a0[j], dg);
     if (lane < K) Lw[j * LS + lane] = a0[j];
-#if UWVKF_CHOL_SHFL_NEXT
-    // the next column is the only one the critical path needs at once: its multiplier L[j+1][j] comes by shuffle, the
-    // columns behind it through shared memory as before
-    if (j + 1 < K) {
-      const double ln = bcast(a0[j], j + 1);
-      a0[j + 1] = fma(-a0[j], ln, a0[j + 1]); a1[j + 1] = fma(-a1[j], ln, a1[j + 1]);
-    }
-    constexpr int CN = 2;
-#else
-    constexpr int CN = 1;
-#endif
     __syncwarp();
     {
-      int c = j + CN;
+      int c = j + 1;
       if (((j * LS + c) & 1) && c < K) {
         const double l = Lw[j * LS + c];
         a0[c] = fma(-a0[j], l, a0[c]); a1[c] = fma(-a1[j], l, a1[c]); ++c;
@@ -504,6 +491,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll 4
     for (int k = lane; k < NV; k += 32)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_saddr + 16u * k), "l"(src + 16 * k) : "memory");
+    // the filter's small inputs ride in the same group, so no global-memory round trip is left inside the iteration
+    if (HAS_PREDICT && lane < 3)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(w_saddr + 8u * (C::O_IN + lane)), "l"(a.rot_rate + ff * 3 + lane) : "memory");
+    if (KIND != M_NONE && lane >= 4 && lane < 4 + C::MF::M)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(w_saddr + 8u * (C::O_IN + lane)), "l"(opu.z + ff * C::MF::M + (lane - 4)) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   {
@@ -551,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== predict (k = 15) ====================================================
     if constexpr (HAS_PREDICT) {
       constexpr int K = 15;
-      const double *wm_g = a.rot_rate + f * 3;
+      const double *wm_g = w + C::O_IN;
       PH(0);
       double a0[K], a1[K];
       const bool spd15 = chol_panel<K>(S, Lw, lane, a0, a1);
@@ -677,7 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       if (go) {
         bool bad = false;
 #pragma unroll
-        for (int k = 0; k < M; ++k) { z[k] = opu.z[f * M + k]; bad |= isnan(z[k]); }
+        for (int k = 0; k < M; ++k) { z[k] = (w + C::O_IN + 4)[k]; bad |= isnan(z[k]); }
 #pragma unroll
         for (int k = 0; k < M * M; ++k) { Rm[k] = opu.Rdev ? opu.Rdev[f * M * M + k] : opu.R[k]; bad |= isnan(Rm[k]); }
         if (bad) { st |= ST_NAN_MEAS; go = false; }
