@@ -103,6 +103,10 @@ struct FusedCfg {
 
 // Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
 // clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
+#ifndef UWVKF_TUB      // trailing-pass pipeline of the kernels with a predict: columns per batch, batches in flight
+#define UWVKF_TUB 6
+#define UWVKF_TDEPTH 2
+#endif
 #ifndef UWVKF_TRAIL_PREFETCH_L1
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
@@ -362,7 +366,7 @@ struct RowData {
 // x0 on lanes 21..31 (rows 21..31); columns b <= 20 need a second, short access for the rows b..20 ("secondary" row x0 of lanes
 // <= 20).  No entry -> (row, column) table, no gathers, no dependent address arithmetic: every column is independent of every
 // other, so the loads of a whole batch of columns are in flight before the first is consumed.
-template <bool AP, bool AK, int KP, int M>
+template <bool AP, bool AK, int KP, int M, int UB, int DEPTH>
 __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const double *Qs, const double *KC, const double (&f)[2],
                                               const double (&ks)[2][3], double q2add, int lane) {
   const bool lo = lane <= 20;
@@ -385,14 +389,15 @@ __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const dou
   };
   // Inactive lanes (rows above the diagonal of column b) read the diagonal entry instead and their store is predicated off, so
   // neither loads nor arithmetic sit behind a branch.  Loads and stores are volatile asm: their program order is the issue order,
-  // which lets the loop below keep the loads of batch i + 1 in flight while batch i is computed and stored (software pipeline;
-  // the triangle was pulled into L2 at the top of the filter's iteration).
-  constexpr int UB = 6, NB = (N - KP + UB - 1) / UB;
+  // which lets the loop below keep the loads of DEPTH - 1 further batches of UB columns in flight while a batch is computed and
+  // stored (software pipeline; the triangle was pulled into L2 at the top of the filter's iteration, and an L2 hit still costs
+  // several hundred cycles).  The register-hungry predict kernels run 6 x 2, the update-only kernels 8 x 3.
+  constexpr int NB = (N - KP + UB - 1) / UB;
   constexpr int NS = KP <= 20 ? 21 - KP : 0;   // columns that also have secondary rows (b .. 20 on lanes <= 20)
   double vS[NS > 0 ? NS : 1];
 #pragma unroll
   for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lo && lane >= KP + u) ? lane : KP + u));
-  double v[2][UB];
+  double v[DEPTH][UB];
   auto load = [&](int i, double (&dst)[UB]) {
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
@@ -410,10 +415,12 @@ __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const dou
       }
     }
   };
-  load(0, v[0]);
+#pragma unroll
+  for (int i = 0; i < DEPTH - 1; ++i)
+    if (i < NB) load(i, v[i]);
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
-    if (i + 1 < NB) load(i + 1, v[(i + 1) & 1]);
+    if (i + DEPTH - 1 < NB) load(i + DEPTH - 1, v[(i + DEPTH - 1) % DEPTH]);
     if (i == 0) {
 #pragma unroll
       for (int u = 0; u < NS; ++u) {
@@ -423,7 +430,7 @@ __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const dou
         stcs_if(actS, gS + coloff(b) + rowS, entry(b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2]));
       }
     }
-    finish(i, v[i & 1]);
+    finish(i, v[i % DEPTH]);
   }
 }
 
@@ -978,14 +985,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       double *gS = blk + OFF_S;
       const double q2add = dt2 * add;
       constexpr int MM_ = (KIND == M_NONE) ? 1 : C::MF::M;
+      constexpr int TUB = HAS_PREDICT ? UWVKF_TUB : 8, TDEPTH = HAS_PREDICT ? UWVKF_TDEPTH : 3;
       if constexpr (KIND == M_NONE) {
-        trailing_pass<true, false, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+        trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
       } else if constexpr (!HAS_PREDICT) {
-        trailing_pass<false, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+        trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
       } else {
-        if (predicted && updated) trailing_pass<true, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
-        else if (predicted) trailing_pass<true, false, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
-        else trailing_pass<false, true, KP, MM_>(gS, Qs, KC, frow, ksr, q2add, lane);
+        if (predicted && updated) trailing_pass<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
+        else if (predicted) trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
+        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
       }
     }
     else {

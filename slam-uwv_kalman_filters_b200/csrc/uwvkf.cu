@@ -250,7 +250,10 @@ namespace {
 #ifndef UWVKF_FUSED_MAX_WARPS
 #define UWVKF_FUSED_MAX_WARPS 12
 #endif
-constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS;
+#ifndef UWVKF_UPDATE_WARPS
+#define UWVKF_UPDATE_WARPS UWVKF_FUSED_MAX_WARPS
+#endif
+constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS, kUpdateMaxWarps = UWVKF_UPDATE_WARPS;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
 }  // namespace
@@ -334,7 +337,8 @@ template <int HP, int KIND>
 constexpr int fused_warps() {
   using C = pose::FusedCfg<HP, KIND>;
   int w = (232448 - C::CTA * 8) / (C::TOTAL * 8);
-  return w > kFusedMaxWarps ? kFusedMaxWarps : w;
+  const int cap = HP ? kFusedMaxWarps : kUpdateMaxWarps;   // update-only kernels carry far less register state
+  return w > cap ? cap : w;
 }
 template <int HP, int KIND>
 int launch_fused(uwvkf_handle h, const pose::Launch &L) {

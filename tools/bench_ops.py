@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--small-filters", type=int, default=1 << 20)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--fast-only", action="store_true", help="skip the dense paths (body efforts, visual markers) and the small filters")
     args = ap.parse_args()
     import torch
     pkg = importlib.import_module("slam-uwv_kalman_filters_b200")
@@ -87,6 +88,10 @@ def main():
     timeit("pose update adcp", upd(pkg.POSE_WATER_VELOCITY, d["adcp"], syn.R_ADCP, np.array([0.5])), B, P, ukf)
     timeit("pose fused predict+DVL", lambda: ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
                                                                   syn.R_DVL, memspace=pkg.DEVICE), B, P, ukf)
+    if args.fast_only:
+        if args.out:
+            json.dump(res, open(args.out, "w"), indent=1)
+        return
     # dense paths (no prefix structure): body efforts (Fossen model per sigma point) and visual markers (59-DOF augmented state)
     ukf.set_model_parameters(syn.uwv_params_flat())
     eff = torch.from_numpy(np.tile(np.array([12.0, -3.0, 1.5, 0.0, 0.0, 0.4]), (B, 1))).to(dev)
