@@ -82,6 +82,7 @@ def load_library():
         lib.uwvkf_graph_launch.argtypes = [C.c_void_p]
         lib.uwvkf_graph_destroy.argtypes = [C.c_void_p]
         lib.uwvkf_debug_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         vp, ci = C.c_void_p, C.c_int
         lib.uwvkf_velocity_setup_motion_model.argtypes = [vp, vp]
         lib.uwvkf_velocity_set_gyro.argtypes = [vp, vp, ci]
@@ -427,6 +428,13 @@ class PoseUKFBatch(_FilterBatch):
         assert rows.ndim == 2 and rows.shape[1] == 8
         out = np.empty((rows.shape[0], 4))
         self._ck(self._lib.uwvkf_debug_eval(self._h, int(what), _ptr(rows), _ptr(out), rows.shape[0]))
+        return out
+
+    def debug_phase_cycles(self, reset=False):
+        """Per-phase latency table of the fused kernel; only a -DUWVKF_PHASE_TIMING build (tools/phase_timing.py) fills it,
+        the product library raises."""
+        out = np.zeros(40, dtype=np.uint64)
+        self._ck(self._lib.uwvkf_debug_phase_cycles(self._h, out.ctypes.data, int(bool(reset))))
         return out
 
     def reset_with_external_pose(self, pose7):

@@ -74,3 +74,9 @@ def test_tensor_path_warp_sum(ukf):
     assert (np.abs(out[:, 1] - ref) / scale).max() < 1e-15
     # every lane of a warp receives the same value
     assert np.array_equal(out[:, 0].reshape(-1, 32), np.repeat(out[::32, 0], 32).reshape(-1, 32))
+
+
+def test_phase_probe_is_absent_from_the_product_build(ukf, pkg):
+    """uwvkf_debug_phase_cycles only works in a -DUWVKF_PHASE_TIMING build (tools/phase_timing.py); the product library says so."""
+    with pytest.raises(pkg.UwvkfError):
+        ukf.debug_phase_cycles()

@@ -20,11 +20,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "build", "libuwvkf_timing.so")
 PHASES = [
     "wait prefix / prefetch / offsets", "predict: chol15", "predict: sigma points (tmerc, boxplus)", "predict: SO3 mean loop",
-    "predict: boxminus + S_oo + A", "predict: solve A L^-1", "predict: G Sigma", "predict: Q_oo, new mean", "predict: couple3 x2",
-    "predict: panel scaling + Q", "predict: ori rows, mu", "update: z, R", "update: chol9", "update: sigma points h(x)",
-    "update: mean", "update: S_zz + B", "update: solve B L^-1", "update: G Sigma", "update: S^-1, gate, gains, K tables",
+    "predict: boxminus + S_oo + A", "-", "predict: A Lp^T", "predict: Q_oo, new mean", "-",
+    "predict: panel F Sigma F^T + Q", "predict: ori rows, mu", "update: z, R", "update: chol9", "update: sigma points h(x)",
+    "update: mean", "update: S_zz + B", "-", "update: B Lp^T", "update: S^-1, gate, gains, K tables",
     "update: panel downdate", "apply_delta: chol6", "apply_delta: sigma points", "apply_delta: SO3 mean loop",
-    "apply_delta: boxminus + S_oo + A", "apply_delta: solve", "apply_delta: G Sigma", "apply_delta: ori rows, mu",
+    "apply_delta: boxminus + S_oo + A", "-", "apply_delta: A Lp^T", "apply_delta: ori rows, mu",
     "(between update and write back)", "write back panel + next prefix", "trailing pass + status",
 ]
 
@@ -100,6 +100,8 @@ def main():
            "sampled_filter_steps": n, "cycles_per_filter_step": tot / n, "phases": {}}
     print(f"{B} filters, {res['ms_per_step_instrumented']:.3f} ms/step (instrumented), {tot / n:.0f} cycles per filter-step per warp")
     for k, name in enumerate(PHASES):
+        if name == "-":
+            continue
         c = float(out[k]) / n
         res["phases"][name] = c
         print(f"  {k:2d} {name:42s} {c:9.0f} cycles  {100 * c * n / tot:5.1f} %")
