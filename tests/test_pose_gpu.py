@@ -550,3 +550,66 @@ def test_matches_committed_golden_sequence(pkg, syn, scen):
         gmu, gcov = ukf.get_state()
         assert_parity(gmu, gcov, mus[s], covs[s], f"golden step {s}")
     ukf.close()
+
+
+def test_update_rolls_back_when_the_downdate_loses_definiteness(pkg, syn, scen):
+    """A (numerically accepted, physically invalid) negative R makes K S K^T overshoot: the downdated position block is not
+    positive definite, apply_delta cannot draw sigma points, and the engine must leave the filter as it was (status bit set), alone
+    and after a predict in the same launch.  The oracle flags the same filters."""
+    B = 12
+    ukf, filt, off = _dense_state(pkg, syn, scen, B)
+    ref, _, _ = _dense_state(pkg, syn, scen, B)
+    mu, cov = ukf.get_state()
+    bad = np.zeros(B, dtype=bool); bad[[0, 5, 11]] = True
+    R = np.stack([(-0.9 * cov[f][0:2, 0:2]) if bad[f] else 0.25 * np.eye(2) for f in range(B)])
+    z = mu[:, 0:2] + 0.05
+    w = syn.pose_inputs(filt, 4)["gyro"]
+    ukf.integrate_measurement(pkg.POSE_XY, z, R)
+    gmu, gcov = ukf.get_state()
+    st = ukf.get_status()
+    assert (st[bad] & pkg.ST_NOT_SPD).all() and not (st[~bad] & pkg.ST_NOT_SPD).any()
+    assert np.array_equal(gmu[bad], mu[bad])
+    for f in np.nonzero(bad)[0]:
+        assert cov_err(gcov[f], cov[f]) < 1e-13                      # panel restored by the inverse rank-2 update
+        assert np.array_equal(gcov[f][15:, 15:], cov[f][15:, 15:])   # trailing triangle never touched
+    omu, ocov, sts = oracle_update(orc.XY, mu, cov, scen, z, R, None, w)
+    assert (sts[bad] & 1).all() and not (sts[~bad] & 1).any()
+    assert_parity(gmu[~bad], gcov[~bad], omu[~bad], ocov[~bad], "XY update next to rolled-back filters")
+    # the same inside a fused launch: predict + refused update == predict alone
+    ukf.set_state(mu, cov); ref.set_state(mu, cov)
+    ukf.clear_status()
+    ukf.predict_update(DT, w, pkg.POSE_XY, z, R)
+    ref.integrate_rotation_rate(w); ref.prediction_step(DT)
+    gmu, gcov = ukf.get_state()
+    pmu, pcov = ref.get_state()
+    assert (ukf.get_status()[bad] & pkg.ST_NOT_SPD).all()
+    assert np.array_equal(gmu[bad], pmu[bad])
+    for f in np.nonzero(bad)[0]:
+        assert cov_err(gcov[f], pcov[f]) < 1e-13
+    ukf.close(); ref.close()
+
+
+@pytest.mark.parametrize("B", [1, 13, 1776 + 29])
+def test_ragged_batch_sizes(pkg, syn, scen, B):
+    """Batches that do not fill the persistent grid (12 warps x #SMs) evenly: first / last filters against the oracle, and the
+    fused step against separate launches for every filter."""
+    a, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    b, *_ = make_batch(pkg, syn, scen, B)
+    for s in range(1, 3):
+        inp = syn.pose_inputs(filt, s)
+        a.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        b.integrate_rotation_rate(inp["gyro"]); b.prediction_step(DT)
+        b.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    assert not a.get_status().any()
+    pick = sorted(set([0, B - 1, B // 2]))
+    inp = syn.pose_inputs(filt, 1)
+    omu, ocov = oracle_predict(mu[pick], cov[pick], scen, inp["gyro"][pick], off[pick])
+    omu, ocov, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, inp["dvl"][pick], syn.R_DVL, None, inp["gyro"][pick])
+    inp2 = syn.pose_inputs(filt, 2)
+    omu, ocov = oracle_predict(omu, ocov, scen, inp2["gyro"][pick], off[pick])
+    omu, ocov, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, inp2["dvl"][pick], syn.R_DVL, None, inp2["gyro"][pick])
+    assert_parity(ma[pick], ca[pick], omu, ocov, f"two fused steps, batch of {B}")
+    a.close(); b.close()
