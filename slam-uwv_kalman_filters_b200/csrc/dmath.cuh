@@ -127,10 +127,13 @@ __device__ __forceinline__ void cos_sinc_sqrt(double x2, double &c, double &s) {
     sincos(x, &sn, &cs);
     c = cs;
     s = sn / x;
-  } else if (x2 >= 1.220703125e-4) {
-    // between MTK's series bound eps^(1/4) = 2^-13 and 1/16 the reference calls cos/sin of sqrt(x2); the Taylor
-    // polynomials below (truncation < 3e-20) return the same doubles to 1 ulp without sqrt / sincos / division.
-    // Even / odd split (Estrin) in y = x2^2: half the dependent depth of a plain Horner chain.
+  } else {
+    // Below 1/16 ONE polynomial serves every lane.  MTK switches to its three-term series (cos: 1 - x2/2 + x2^2/24 - x2^3/720,
+    // sinc: 1 - x2/6 + x2^2/120 - x2^3/5040) below eps^(1/4) = 2^-13 and calls cos / sin of sqrt(x2) above; the Taylor
+    // polynomials here (truncation < 3e-20) return the libm doubles to 1 ulp above that bound, and below it their extra terms
+    // (x2^4 / 40320 < 6e-21) vanish against the 1.1e-16 ulp of the result: the same doubles as the three-term series.  A
+    // sigma-point set always mixes both ranges (the centre point has x2 = 0), so a second branch here would make every
+    // boxplus of the kernel divergent.  Even / odd split (Estrin) in y = x2^2: half the dependent depth of a Horner chain.
     const double y = x2 * x2;
     double ce = fma(y, 1.0 / 479001600.0, 1.0 / 40320.0);       // x2^2, x2^4, x2^6 terms of cos: 1/24, 1/40320, 1/12!
     ce = fma(ce, y, 1.0 / 24.0);
@@ -144,11 +147,6 @@ __device__ __forceinline__ void cos_sinc_sqrt(double x2, double &c, double &s) {
     so = fma(so, y, -1.0 / 5040.0);
     so = fma(so, y, -1.0 / 6.0);
     s = fma(se, y, fma(so, x2, 1.0));
-  } else {
-    // MTK's three-term series (cos: 1 - x2/2 + x2^2/24 - x2^3/720, sinc: 1 - x2/6 + x2^2/120 - x2^3/5040) in Horner form:
-    // the same truncated sums to 1 ulp with a third of the dependent depth of the term recurrence
-    c = fma(fma(fma(x2, -1.0 / 720.0, 1.0 / 24.0), x2, -0.5), x2, 1.0);
-    s = fma(fma(fma(x2, -1.0 / 5040.0, 1.0 / 120.0), x2, -1.0 / 6.0), x2, 1.0);
   }
 }
 __device__ __forceinline__ Quat so3_exp(const Vec3 &v, double scale) {

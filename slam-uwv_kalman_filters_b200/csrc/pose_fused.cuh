@@ -314,14 +314,13 @@ __device__ __forceinline__ void process_panel(double *S, const double *Qs, const
       for (int h = 0; h < 2; ++h) {
         const int x = lane + 32 * h;
         const int cox = h ? coloff(x < N ? x : 0) : colane;
-        double val = 0.0;
-        if (x >= b && x < N && !(x >= 3 && x < 6)) {
-          val = fma(f[h] * fb, S[cb + x], Qs[cb + x]);
-          val = fma(dt * f[h], S[x >= pb ? cpb + x : cox + pb], val);
-          if (h == 0 && rp) {
-            val = fma(dt * fb, S[cb + px], val);
-            val = fma(dt2, S[px >= pb ? cpb + px : copx + pb], val);
-          }
+        // every load is unconditional (inactive lanes read other entries of the warp's own shared-memory region and drop the
+        // result): a branch per entry would put one shared-memory round trip per entry on the critical path
+        double val = fma(f[h] * fb, S[cb + x], Qs[cb + x]);
+        val = fma(dt * f[h], S[x >= pb ? cpb + x : cox + pb], val);
+        if (h == 0) {
+          const double t1 = S[cb + px], t3 = S[px >= pb ? cpb + px : copx + pb];
+          val = rp ? fma(dt2, t3, fma(dt * fb, t1, val)) : val;
         }
         nv[i][h] = val;
       }
