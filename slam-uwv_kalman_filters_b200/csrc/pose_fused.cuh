@@ -596,20 +596,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
         const double (&rdf)[2] = frow;
         // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
+        // (branch-free: the three cases sit on different lanes of the same warp)
         auto new_mean = [&](int sidx_, double offv) {
-          const double xv = mu[sidx_];
-          double rate;
-          if (sidx_ < P_ORI) rate = mu[P_VEL + sidx_];
-          else if (sidx_ >= P_VEL && sidx_ < P_ACC) rate = mu[sidx_ + 3];
-          else {
-            const double o = ((sidx_ >= P_INERTIA && sidx_ < P_WV) || sidx_ == P_RHO) ? offv : otab[sidx_];
-            rate = mtau[sidx_] * (xv - o);
-          }
-          return xv + dt * rate;
+          const int sc = sidx_ < DIM ? sidx_ : 0;
+          const double xv = mu[sc];
+          const bool kin = sc < P_ORI || (sc >= P_VEL && sc < P_ACC);          // position <- velocity, velocity <- acceleration
+          const double partner = mu[kin ? sc + (sc < P_ORI ? P_VEL : 3) : sc];
+          const double o = ((sc >= P_INERTIA && sc < P_WV) || sc == P_RHO) ? offv : otab[sc];
+          const double rate = kin ? partner : mtau[sc] * (xv - o);
+          return fma(dt, rate, xv);
         };
-        double nm0 = 0, nm1 = 0;
-        if (x0 < P_ORI || x0 >= P_VEL) nm0 = new_mean(x0, off0);
-        if (x1 < DIM) nm1 = new_mean(x1, off1);
+        const double nm0 = new_mean(x0, off0), nm1 = new_mean(x1, off1);   // consumed only where the row is not the orientation
         __syncwarp();
         PH(7);
         // panel <- F panel F^T + dt^2 Q on the affine rows (couplings and scaling in one pass)
