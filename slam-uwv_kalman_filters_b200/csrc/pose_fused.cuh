@@ -1,15 +1,19 @@
-// PoseUKF fused step kernel, version 2 ("panel + stream").
+// PoseUKF fused step kernel ("panel + stream"; DESIGN.md sections 3-6 give the algebra, the layout and the measurements).
 //
-// Same mathematics as pose_engine.cuh (prefix-structured unscented transform) with a
-// different residency plan: every op of the fast path (predict k=15, DVL k=9, XY/Z k<=3, acceleration k=19,
-// apply_delta k=6) reads and writes only the first KP columns of Sigma -- the PANEL, a prefix of the
-// column-packed block.  The trailing (53-KP)^2/2 entries are touched by exactly one elementwise expression,
+// Same mathematics as pose_engine.cuh (prefix-structured unscented transform) with a different residency plan: every op of
+// the fast path (predict k=15, DVL k=9, XY/Z k<=3, acceleration k=19, apply_delta k=6) reads and writes only the first KP
+// columns of Sigma -- the PANEL, a prefix of the column-packed block, staged in shared memory one filter ahead by cp.async
+// together with mu and the filter's inputs.  The trailing (53-KP)^2/2 entries are touched by exactly one elementwise expression,
 //     Sigma_new[a][b] = f_a f_b Sigma_old[a][b] + dt^2 Q[a][b] - sum_c (K S)[a][c] K[b][c],
-// so they never enter shared memory: after the panel work is done each warp streams them HBM -> registers ->
-// HBM once, column by column, with the per-row factors (f_a, (KS)_a) held in registers by the lane that owns
-// row a and the per-column factors (f_b, K_b) read as one shared-memory broadcast.  Shared memory per warp drops
-// from 17.6 KB to ~10.8 KB (more resident warps) and the two 1431-entry passes of v1 (LUT decode + 8 scattered
-// shared loads per entry) disappear.
+// so they never enter shared memory: after the panel work each warp streams them HBM -> registers -> HBM once, column by
+// column (trailing_pass).  One warp per filter; a lane owns the covariance rows x0 = lane and x1 = lane + 32 in EVERY phase:
+//   * chol_panel: Cholesky of the leading block carried over the whole panel, both rows of the panel factor in registers --
+//     cross-covariances are dot products of registers with broadcast rows of the sigma-point deviations (no triangular
+//     solves, no re-read of Sigma);
+//   * process_panel / downdate / trailing_pass: row factors (f_a, (K S)_a) in registers, column factors ({K_b, f_b}, one
+//     AoS table per warp) as broadcast 128-bit shared loads;
+//   * lanes double as sigma points (2k+1 <= 39 distinct points, the rest is a multiplicity of the centre) for the models;
+//     warp sums run on the FP64 tensor path (wsum).
 #pragma once
 #include "pose_engine.cuh"
 #include <type_traits>
@@ -101,15 +105,16 @@ struct FusedCfg {
   static constexpr int CTA = C_OTAB + 56;
 };
 
-// Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
-// clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
+// Tuning switches (tools/build_variant.sh builds variants; DESIGN.md section 6 lists what was measured)
 #ifndef UWVKF_TUB      // trailing-pass pipeline of the kernels with a predict: columns per batch, batches in flight
 #define UWVKF_TUB 6
 #define UWVKF_TDEPTH 2
 #endif
-#ifndef UWVKF_TRAIL_PREFETCH_L1
+#ifndef UWVKF_TRAIL_PREFETCH_L1   // 1: pull the trailing triangle into L1 instead of L2 at the top of a filter (measured: no gain)
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
+// Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
+// clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
 #ifdef UWVKF_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[40];
 #define PH_DECL long long ph_t = clock64();
@@ -155,6 +160,7 @@ __device__ __forceinline__ double wsum(double v) {
   const double s = d0 + d1;
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
       : "=d"(e0), "=d"(e1) : "d"(s), "d"(one), "d"(zero), "d"(zero));
+  (void)e1;
   return e0;
 }
 
@@ -348,13 +354,6 @@ __device__ __forceinline__ void process_panel(double *S, const double *Qs, const
     }
   }
 }
-
-// per-lane row data for the rows x0 = lane and x1 = lane + 32
-struct RowData {
-  double f[2];       // diagonal of the affine process map (1 when no predict)
-  double ks[2][3];   // (K S) rows of the accepted update (0 when none)
-  double kk[2][3];   // K rows
-};
 
 // Trailing triangle (columns >= KP of the packed covariance, a contiguous suffix of the filter block), streamed HBM -> registers
 // -> HBM once:   s <- f_a f_b s + dt^2 Q_ab - sum_c (K S)_ac K_bc.
