@@ -395,10 +395,11 @@ class PoseUKFBatch(_FilterBatch):
         """integrateMeasurement(const RotationRate&) (src/PoseUKF.cpp:492-496)."""
         self._ck(self._lib.uwvkf_pose_set_rotation_rate(self._h, _ptr(_f64(w)), memspace))
 
-    def integrate_measurement(self, kind, z, R, aux=None, valid=None, memspace=HOST):
-        """integrateMeasurement(<kind>) (src/PoseUKF.cpp:476-611). R: [m,m] shared or [B,m,m]."""
+    def integrate_measurement(self, kind, z, R, aux=None, valid=None, memspace=HOST, per_filter_R=None):
+        """integrateMeasurement(<kind>) (src/PoseUKF.cpp:476-611). R: [m,m] shared or [B,m,m] (per_filter_R says which when R
+        is a raw device pointer)."""
         z, R, aux = _f64(z), _f64(R), _f64(aux)
-        per = 0 if isinstance(R, int) else int(R.ndim == 3)
+        per = int(per_filter_R) if per_filter_R is not None else (0 if isinstance(R, int) else int(R.ndim == 3))
         if valid is not None and not isinstance(valid, int):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_update(self._h, kind, _ptr(z), _ptr(R), per, _ptr(aux), _ptr(valid), memspace))
@@ -411,10 +412,10 @@ class PoseUKFBatch(_FilterBatch):
                                                       _ptr(_f64(marker_pose)), _ptr(_f64(cov_marker)), _ptr(_f64(camera)),
                                                       _ptr(_f64(cam_in_imu)), _ptr(_u8(valid)), memspace))
 
-    def predict_update(self, dt, w, kind, z, R, aux=None, valid=None, memspace=HOST):
+    def predict_update(self, dt, w, kind, z, R, aux=None, valid=None, memspace=HOST, per_filter_R=None):
         """Fused predictionStep(dt) + integrateMeasurement(kind) in one kernel (one HBM round trip)."""
         w, z, R, aux = _f64(w), _f64(z), _f64(R), _f64(aux)
-        per = 0 if isinstance(R, int) else int(R.ndim == 3)
+        per = int(per_filter_R) if per_filter_R is not None else (0 if isinstance(R, int) else int(R.ndim == 3))
         if valid is not None and not isinstance(valid, int):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_predict_update(self._h, float(dt), _ptr(w), kind, _ptr(z), _ptr(R), per, _ptr(aux),

@@ -32,15 +32,37 @@ constexpr int M_NONE = -1;
 //   P_xz = Sigma[:, :K] L11^-T (B - L_T^T C^T) + Sigma[:, T] C^T,         L_T = Sigma[T, :K] L11^-T.
 template <int KIND> struct FMeas : Meas<KIND> {
   static constexpr int NT = 0;
+  static constexpr int KPMIN = 0;   // smallest panel the kernel must keep in shared memory (tail coordinates it wants resident)
   __host__ __device__ static constexpr int tail(int) { return 0; }
   __host__ __device__ static constexpr int slot(int) { return 0; }
   __device__ static void tail_jac(const double *, const double *, const Params &, double *) {}
 };
-// (The accelerometer model q^-1 (a + g e_z) + b_a also fits this form -- prefix 6, tail = acceleration, bias, gravity -- and
-// was measured: parity green, but the 7-coordinate tail (49 Sigma_TT entries, 14 trailing-triangle loads per lane in the middle
-// of the critical path) costs what the smaller Cholesky saves, 2.12 ms vs 2.08 ms per 262,144 filters, so it stays prefix 19.)
+// The accelerometer model q^-1 (a + g e_z) + b_a (src/PoseUKF.cpp:125-131): prefix 6 (the orientation), tail = acceleration,
+// accelerometer bias, gravity.  The panel is kept 19 columns wide so that every tail row / column is resident in shared memory;
+// what shrinks is the factorisation (6 instead of 19 columns) and the sigma-point set (13 instead of 39 points).
+template <> struct FMeas<M_ACCELERATION> {
+  static constexpr int K = 6, M = 3, NT = 7, KPMIN = 19;
+  __host__ __device__ static constexpr int tail(int r) { return r < 3 ? T_ACC + r : (r < 6 ? T_BA + (r - 3) : T_G); }
+  __host__ __device__ static constexpr int slot(int t) { return t < T_BG ? t - T_ACC : (t < T_G ? t - T_BA + 3 : 6); }
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+    Meas<M_ACCELERATION>::eval(mu, d, aux, P, o);
+  }
+  __device__ static void tail_jac(const double *mu, const double *, const Params &, double *C) {   // C[c * NT + r]
+    double Rm[9];
+    qmat(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Rm);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        C[c * 7 + r] = Rm[r * 3 + c];             // d/d acceleration: R^T
+        C[c * 7 + 3 + r] = (c == r) ? 1.0 : 0.0;   // d/d bias
+      }
+      C[c * 7 + 6] = Rm[2 * 3 + c];               // d/d gravity: R^T e_z
+    }
+  }
+};
 template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, q, gravity) = 19, tail = water density
-  static constexpr int K = 19, M = 1, NT = 1;
+  static constexpr int K = 19, M = 1, NT = 1, KPMIN = 0;
   __host__ __device__ static constexpr int tail(int) { return T_RHO; }
   __host__ __device__ static constexpr int slot(int) { return 0; }
   template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
@@ -52,7 +74,7 @@ template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, 
   }
 };
 template <> struct FMeas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151: prefix (q, v) = 9, tail = wv, wv_below, bias_adcp
-  static constexpr int K = 9, M = 2, NT = 6;
+  static constexpr int K = 9, M = 2, NT = 6, KPMIN = 0;
   __host__ __device__ static constexpr int tail(int r) { return T_WV + r; }
   __host__ __device__ static constexpr int slot(int t) { return t - T_WV; }
   template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
@@ -81,7 +103,9 @@ struct FusedCfg {
   static constexpr int NT = (KIND == M_NONE) ? 0 : MF::NT;
   static constexpr int KA = (KIND == M_NONE) ? 0 : 6;                       // apply_delta prefix
   static constexpr int K0 = HAS_PREDICT ? 15 : 0;
-  static constexpr int KP = (K0 > KM ? (K0 > KA ? K0 : KA) : (KM > KA ? KM : KA));   // panel width
+  static constexpr int KPM = (KIND == M_NONE) ? 0 : MF::KPMIN;
+  static constexpr int KP0 = (K0 > KM ? (K0 > KA ? K0 : KA) : (KM > KA ? KM : KA));
+  static constexpr int KP = KP0 > KPM ? KP0 : KPM;                          // panel width
   static constexpr int PANEL = KP * N - (KP * (KP - 1)) / 2;                // doubles in the panel
   static constexpr int PANEL_E = ((PANEL + 1) / 2) * 2;
   static constexpr int KL = KP;                                             // largest leading factor
@@ -780,26 +804,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
             for (int r = 0; r < NT; ++r) U[c] = fma(Ct[c * NT + r], lt[r], U[c]);
           }
-          double stt[NT * NT];
+          // C Sigma_TT C^T with ONE ROW of Sigma_TT per lane (lane r < NT): w_r = Sigma_TT[r, :] C^T, then
+          // (C Sigma_TT C^T)[i][b] = sum_r C[i][r] w_r[b] rides in the same warp sum as -U U^T.  (Every lane forming all of
+          // Sigma_TT and the full triple product costs NT^2 loads and 2 NT^2 FMAs per entry of S_zz.)
+          const int rr = lane < NT ? lane : 0;
+          int tr = MM::tail(0);
 #pragma unroll
-          for (int a2 = 0; a2 < NT; ++a2)
+          for (int k = 1; k < NT; ++k) tr = (rr == k) ? MM::tail(k) : tr;
+          double wrow[M], crow[M];
 #pragma unroll
-            for (int b2 = 0; b2 <= a2; ++b2) stt[a2 * NT + b2] = stt[b2 * NT + a2] = sig(MM::tail(a2), MM::tail(b2));
+          for (int b = 0; b < M; ++b) wrow[b] = 0.0;
+#pragma unroll
+          for (int b2 = 0; b2 < NT; ++b2) {
+            const int tb = MM::tail(b2);
+            const double sv = (tr >= tb) ? sig(tr, tb) : sig(tb, tr);
+#pragma unroll
+            for (int b = 0; b < M; ++b) wrow[b] = fma(sv, Ct[b * NT + b2], wrow[b]);
+          }
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            double c = Ct[i * NT];
+#pragma unroll
+            for (int k = 1; k < NT; ++k) c = (rr == k) ? Ct[i * NT + k] : c;
+            crow[i] = lane < NT ? c : 0.0;
+          }
 #pragma unroll
           for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int b = 0; b <= i; ++b) {
-              double cs = 0;
-#pragma unroll
-              for (int a2 = 0; a2 < NT; ++a2) {
-                double t2 = 0;
-#pragma unroll
-                for (int b2 = 0; b2 < NT; ++b2) t2 = fma(stt[a2 * NT + b2], Ct[b * NT + b2], t2);
-                cs = fma(Ct[i * NT + a2], t2, cs);
-              }
-              const double uu = wsum(U[i] * U[b]);
-              Szz[i * M + b] += cs - uu;
-              if (b != i) Szz[b * M + i] += cs - uu;
+              const double t2 = wsum(fma(crow[i], wrow[b], -(U[i] * U[b])));
+              Szz[i * M + b] += t2;
+              if (b != i) Szz[b * M + i] += t2;
             }
           if (lane < K) {
 #pragma unroll
