@@ -23,6 +23,10 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
+#ifndef UWVKF_DVL_TAIL            // 1: DVL update as prefix 6 + affine tail (velocity): parity green, 2 % slower than prefix 9
+#define UWVKF_DVL_TAIL 0
+#endif
+
 // Measurement traits of the fused kernel: prefix K (tangent coordinates the model reads arbitrarily) plus an AFFINE TAIL
 // of NT tangent coordinates tail(0..NT-1) (ascending, all >= K) that the model reads affinely once the prefix is fixed
 // (slot(t) maps a tail coordinate back to its position in that list).
@@ -61,6 +65,25 @@ template <> struct FMeas<M_ACCELERATION> {
     }
   }
 };
+#if UWVKF_DVL_TAIL
+// DVL model q^-1 v (src/PoseUKF.cpp:117-123): prefix 6 (position, orientation), tail = velocity (affine once q is fixed)
+template <> struct FMeas<M_VELOCITY> {
+  static constexpr int K = 6, M = 3, NT = 3, KPMIN = 9;
+  __host__ __device__ static constexpr int tail(int r) { return T_VEL + r; }
+  __host__ __device__ static constexpr int slot(int t) { return t - T_VEL; }
+  template <class D> __device__ static void eval(const double *mu, D d, const double *aux, const Params &P, double *o) {
+    Meas<M_VELOCITY>::eval(mu, d, aux, P, o);
+  }
+  __device__ static void tail_jac(const double *mu, const double *, const Params &, double *C) {   // C[c * NT + r] = (R^T)[c][r]
+    double Rm[9];
+    qmat(Quat{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]}, Rm);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) C[c * 3 + r] = Rm[r * 3 + c];
+  }
+};
+#endif
 template <> struct FMeas<M_PRESSURE> {   // src/PoseUKF.cpp:107-115: prefix (z, q, gravity) = 19, tail = water density
   static constexpr int K = 19, M = 1, NT = 1, KPMIN = 0;
   __host__ __device__ static constexpr int tail(int) { return T_RHO; }
