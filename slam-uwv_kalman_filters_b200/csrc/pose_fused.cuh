@@ -157,6 +157,9 @@ struct FusedCfg {
 #define UWVKF_TUB 6
 #define UWVKF_TDEPTH 2
 #endif
+#ifndef UWVKF_BULK_WB             // 1: panel write-back as one cp.async.bulk (TMA) copy per filter
+#define UWVKF_BULK_WB 0
+#endif
 #ifndef UWVKF_TRAIL_PREFETCH_L1   // 1: pull the trailing triangle into L1 instead of L2 at the top of a filter (measured: no gain)
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
@@ -1020,6 +1023,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== write back ===========================================================
     PH(27);
     if (predicted || updated) {
+#if UWVKF_BULK_WB
+      if constexpr ((C::PANEL & 1) == 0) {
+        // [mu | panel] goes back as ONE bulk copy (TMA engine, shared -> global): every lane publishes its shared-memory writes
+        // to the async proxy, lane 0 issues the copy and waits until the engine has READ the buffer (the writes to HBM finish
+        // on their own; the buffer is about to be refilled with the next filter's prefix)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(blk), "r"(w_saddr), "r"((unsigned)(NV * 16)) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      } else
+#endif
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(w);
@@ -1061,6 +1078,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[39], 1ull);
 #endif
   }
+#if UWVKF_BULK_WB
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every bulk write has landed before the warp exits
+#endif
 }
 
 }  // namespace pose
