@@ -23,6 +23,9 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
+#ifndef UWVKF_BULK_WB             // 1: panel write-back as one cp.async.bulk (TMA) copy per filter; 2: + second prefix buffer
+#define UWVKF_BULK_WB 0
+#endif
 #ifndef UWVKF_DVL_TAIL            // 1: DVL update as prefix 6 + affine tail (velocity): parity green, 2 % slower than prefix 9
 #define UWVKF_DVL_TAIL 0
 #endif
@@ -137,7 +140,11 @@ struct FusedCfg {
   // per-warp shared layout (doubles)
   static constexpr int O_MU = 0;                   // 56
   static constexpr int O_S = 56;                   // panel (same indexing as the full packed array)
-  static constexpr int O_L = O_S + PANEL_E;
+  // UWVKF_BULK_WB == 2: a second [mu | panel] buffer, so that the bulk write-back of one filter and the prefix fetch of the
+  // next never touch the same shared memory (only where it still leaves room for 12 warps)
+  static constexpr bool DB = (UWVKF_BULK_WB == 2) && ((PANEL & 1) == 0) && (KP <= 15);
+  static constexpr int PBUF = 56 + PANEL_E;        // doubles per prefix buffer
+  static constexpr int O_L = O_S + PANEL_E + (DB ? PBUF : 0);
   static constexpr int O_G = O_L + LSZ;          // per sigma-point pair j: {A[0][j], A[1][j], A[2][j], -}, AoS [KE][4]
   static constexpr int O_KC = O_G + 4 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
                                                    // 128-bit loads hand a whole warp everything column b contributes)
@@ -156,9 +163,6 @@ struct FusedCfg {
 #ifndef UWVKF_TUB      // trailing-pass pipeline of the kernels with a predict: columns per batch, batches in flight
 #define UWVKF_TUB 6
 #define UWVKF_TDEPTH 2
-#endif
-#ifndef UWVKF_BULK_WB             // 1: panel write-back as one cp.async.bulk (TMA) copy per filter
-#define UWVKF_BULK_WB 0
 #endif
 #ifndef UWVKF_TRAIL_PREFETCH_L1   // 1: pull the trailing triangle into L1 instead of L2 at the top of a filter (measured: no gain)
 #define UWVKF_TRAIL_PREFETCH_L1 0
@@ -507,6 +511,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *G = w + C::O_G;
+  unsigned cur = 0;   // prefix buffer of the current filter (double-buffered builds only)
+  (void)cur;
   double *KC = w + C::O_KC, *LTs = w + C::O_LT;
   (void)LTs;
   {
@@ -541,11 +547,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   // panel has been written back, and are waited for at the top of the next iteration, so they fly during the trailing pass.
   constexpr int NV = (56 + C::PANEL_E) / 2;
   const unsigned w_saddr = (unsigned)__cvta_generic_to_shared(w);
-  auto fetch_prefix = [&](long long ff) {
+  auto fetch_prefix = [&](long long ff, unsigned buf) {
     const char *src = reinterpret_cast<const char *>(a.state + ff * BLK);
+    const unsigned dsta = w_saddr + (C::DB ? buf * (8u * C::PBUF) : 0u);
 #pragma unroll 4
     for (int k = lane; k < NV; k += 32)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w_saddr + 16u * k), "l"(src + 16 * k) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta + 16u * k), "l"(src + 16 * k) : "memory");
     // the filter's small inputs ride in the same group, so no global-memory round trip is left inside the iteration
     if (HAS_PREDICT && lane < 3)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(w_saddr + 8u * (C::O_IN + lane)), "l"(a.rot_rate + ff * 3 + lane) : "memory");
@@ -555,11 +562,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   };
   {
     const long long f0 = (long long)blockIdx.x * WARPS + warp;
-    if (f0 < a.B) fetch_prefix(f0);
+    if (f0 < a.B) fetch_prefix(f0, 0u);
   }
 
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
+    if constexpr (C::DB) { mu = w + cur * C::PBUF; S = mu + C::O_S; }
     PH_DECL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -1026,20 +1034,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #if UWVKF_BULK_WB
       if constexpr ((C::PANEL & 1) == 0) {
         // [mu | panel] goes back as ONE bulk copy (TMA engine, shared -> global): every lane publishes its shared-memory writes
-        // to the async proxy, lane 0 issues the copy and waits until the engine has READ the buffer (the writes to HBM finish
-        // on their own; the buffer is about to be refilled with the next filter's prefix)
+        // to the async proxy and lane 0 issues the copy.  With one prefix buffer lane 0 then waits until the engine has READ it
+        // (it is about to be refilled); with two, the next prefix goes to the other buffer, whose own copy -- issued one filter
+        // ago -- is waited for instead (long done).  The writes to HBM finish on their own.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(blk), "r"(w_saddr), "r"((unsigned)(NV * 16)) : "memory");
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(blk),
+                       "r"(w_saddr + (C::DB ? cur * (8u * C::PBUF) : 0u)), "r"((unsigned)(NV * 16)) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (C::DB) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
       } else
 #endif
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
-        const double2 *src = reinterpret_cast<const double2 *>(w);
+        const double2 *src = reinterpret_cast<const double2 *>(mu);
         // if PANEL is odd the last double2 also carries the (unchanged) first trailing entry: it is rewritten by the
         // trailing pass below, which is ordered after this copy by the __syncwarp
 #pragma unroll 4
@@ -1048,7 +1059,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       __syncwarp();
       {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
         const long long fn = f + (long long)gridDim.x * WARPS;
-        if (fn < a.B) fetch_prefix(fn);
+        if (fn < a.B) fetch_prefix(fn, cur ^ 1u);
       }
       // trailing triangle (columns >= KP), see trailing_pass: process map and / or rank-M downdate, whichever happened
       PH(28);
@@ -1067,10 +1078,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       }
     }
     else {
+#if UWVKF_BULK_WB
+      if (C::DB && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other buffer's copy
+#endif
       __syncwarp();
       const long long fn = f + (long long)gridDim.x * WARPS;
-      if (fn < a.B) fetch_prefix(fn);
+      if (fn < a.B) fetch_prefix(fn, cur ^ 1u);
     }
+    if constexpr (C::DB) cur ^= 1u;
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();
     PH(29);
