@@ -2,7 +2,7 @@
 """Drift of the CUDA engine against the CPU oracle over a long free-running sequence (north_star: "drift over 10k steps
 reported").  Both start from the same states and consume the same synthetic inputs; neither is re-synchronised.
 
-  python tools/drift_report.py [--steps 10000] [--filters 8] [--out gpurun_out/drift.json]
+  python tests/drift_report.py [--steps 10000] [--filters 8] [--out gpurun_out/drift.json]
 
 Sequence = BASELINE.json config 3/4 mix: 100 Hz predict + DVL + accelerometer, pressure at 10 Hz, ADCP (gated) at 1 Hz,
 a DVL dropout window.  Reported: max over filters of the relative state error and the relative covariance error (same

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Drift of the small filters (VelocityUKF = BASELINE config 1/2, BottomUKF and IndirectPoseUKF = config 5) against the CPU
-oracle over long free-running sequences; same idea as tools/drift_report.py.
+oracle over long free-running sequences; same idea as tests/drift_report.py.
 
-  python tools/drift_small.py [--steps 10000] [--filters 4] [--out gpurun_out/drift_small.json]
+  python tests/drift_small.py [--steps 10000] [--filters 4] [--out gpurun_out/drift_small.json]
 """
 import argparse
 import importlib
