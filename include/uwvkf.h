@@ -99,7 +99,9 @@ enum uwvkf_pose_param_index {
  * src/IndirectPoseUKF.hpp:44-48): allocates `batch` filters of `filter_kind` on CUDA device `device`. */
 int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out);
 int uwvkf_destroy(uwvkf_handle h);
-/* All work of the handle is ordered on this cudaStream_t (default: the legacy default stream). */
+/* All work of the handle is ordered on this cudaStream_t (default: the legacy default stream).  The old stream is drained
+ * before the switch (staged inputs may still be in flight on it); uwvkf_create returns with all device memory initialised,
+ * so a non-blocking user stream may be used right away. */
 int uwvkf_set_stream(uwvkf_handle h, void *cuda_stream);
 int uwvkf_synchronize(uwvkf_handle h);
 const char *uwvkf_last_error(void);
@@ -137,7 +139,9 @@ int uwvkf_pose_set_model_parameters(uwvkf_handle h, const double *uwv_params);
 /* Markov offsets (inertia 9, lin_damping 9, quad_damping 9, water_density) per filter, host pointer;
  * overrides what uwvkf_set_state latched (src/PoseUKF.cpp:346-349). */
 int uwvkf_pose_set_offsets(uwvkf_handle h, const double *offsets, int64_t first, int64_t count);
-/* integrateMeasurement(const RotationRate&) (src/PoseUKF.cpp:492-496): stores the control input w[B][3]. */
+/* integrateMeasurement(const RotationRate&) (src/PoseUKF.cpp:492-496): stores the control input w[B][3].  NaN in a HOST
+ * w returns UWVKF_ERR_NAN_MEASUREMENT (any batch size; the reference throws); a NaN in a DEVICE w is caught per filter by
+ * the next prediction, which is skipped for that filter with UWVKF_ST_NAN_MEASUREMENT set. */
 int uwvkf_pose_set_rotation_rate(uwvkf_handle h, const double *w, int memspace);
 /* getRotationRate() (src/PoseUKF.cpp:693-699) for every filter: out[B][3], host. */
 int uwvkf_pose_get_rotation_rate(uwvkf_handle h, double *out);
@@ -147,7 +151,8 @@ int uwvkf_predict(uwvkf_handle h, double dt);
  * R_per_filter != 0; aux: per-kind extra arguments shared by the batch (host pointer, may be NULL ->
  * zeros); valid[B] (may be NULL): filters with valid == 0 skip the update (sensor dropout).
  * memspace says where z, R (if per filter) and valid live.  NaN in a HOST z/R returns
- * UWVKF_ERR_NAN_MEASUREMENT like checkMeasurment(); device inputs are checked per filter in the kernel. */
+ * UWVKF_ERR_NAN_MEASUREMENT like checkMeasurment() (every HOST input is scanned, whatever the batch size);
+ * DEVICE inputs are checked per filter in the kernel (UWVKF_ST_NAN_MEASUREMENT, update skipped). */
 int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const double *R, int R_per_filter,
                       const double *aux, const uint8_t *valid, int memspace);
 /* Fused hot path: predictionStep(dt) immediately followed by integrateMeasurement(<kind>) in ONE kernel

@@ -101,13 +101,18 @@ def load_library():
 
 
 def _ptr(a):
-    """numpy array -> host pointer, int -> raw (device) pointer, None -> NULL."""
+    """numpy array -> host pointer, int -> raw (device) pointer, None -> NULL.
+
+    The returned c_void_p keeps a reference to the array, so a converted temporary (`_ptr(_f64([0, 0, 1]))`) stays alive for
+    as long as the pointer object does -- i.e. for the whole foreign call it is an argument of."""
     if a is None:
         return None
     if isinstance(a, int):
         return C.c_void_p(a)
     assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "contiguous numpy array or raw pointer expected"
-    return C.c_void_p(a.ctypes.data)
+    p = C.c_void_p(a.ctypes.data)
+    p._keepalive = a
+    return p
 
 
 def _f64(a):

@@ -14,6 +14,7 @@
 
 namespace uwvkf {
 int fail(int code, const std::string &msg);
+bool any_nan(const double *v, int64_t n);   // host scan (checkMeasurment() of the reference throws on NaN)
 }
 
 #define CK(call)                                                                                      \

@@ -351,6 +351,8 @@ __device__ __forceinline__ bool predict(double *w, const double *Qs, const uint1
   using W = WL<KMAX>;
   constexpr int K = 15;
   double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *T = w + W::T, *fv = w + W::F;
+  // a NaN rotation rate (device-resident control input the host could not scan) would poison the state: refuse the prediction
+  if (isnan(wm_g[0]) || isnan(wm_g[1]) || isnan(wm_g[2])) { status |= ST_NAN_MEAS; return false; }
   if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
   const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
   const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};

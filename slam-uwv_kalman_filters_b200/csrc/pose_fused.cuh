@@ -609,7 +609,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       const double *wm_g = w + C::O_IN;
       PH(0);
       double a0[K], a1[K];
-      const bool spd15 = chol_panel<K>(S, Lw, lane, a0, a1);
+      // a NaN rotation rate (device-resident control input the host could not scan) would poison the state: the prediction
+      // is refused for this filter (status bit), like checkMeasurment() throwing in the reference (src/PoseUKF.cpp:494)
+      const bool wbad = isnan(wm_g[0]) || isnan(wm_g[1]) || isnan(wm_g[2]);
+      const bool spd15 = !wbad && chol_panel<K>(S, Lw, lane, a0, a1);
       PH(1);
       if (spd15) {
         const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         __syncwarp();
         PH(10);
       } else {
-        st |= ST_NOT_SPD;
+        st |= wbad ? ST_NAN_MEAS : ST_NOT_SPD;
       }
     }
 

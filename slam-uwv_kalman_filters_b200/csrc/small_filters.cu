@@ -272,13 +272,9 @@ inline Mat36 mat_of(const double *src, int n) {
   for (int k = 0; k < n; ++k) m.v[k] = src[k];
   return m;
 }
-bool any_nan(const double *v, int64_t n) {
-  for (int64_t k = 0; k < n; ++k) if (std::isnan(v[k])) return true;
-  return false;
-}
 int copy_ctrl(uwvkf_handle h, double *dst, const double *src, int per, int memspace) {
   if (!src) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null input");
-  if (memspace == UWVKF_HOST && h->B <= 1024 && any_nan(src, h->B * per)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "input contains NaN");
+  if (memspace == UWVKF_HOST && any_nan(src, h->B * per)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "input contains NaN");
   CK(cudaMemcpyAsync(dst, src, (size_t)h->B * per * sizeof(double),
                      memspace == UWVKF_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   return UWVKF_OK;
@@ -286,7 +282,7 @@ int copy_ctrl(uwvkf_handle h, double *dst, const double *src, int per, int memsp
 // measurement inputs: stage z (+ valid) on the device, NaN-check small host batches like checkMeasurment()
 int stage_meas(uwvkf_handle h, const double *z, int m, const uint8_t *valid, int memspace, const double **dz, const uint8_t **dv) {
   if (!z) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null measurement");
-  if (memspace == UWVKF_HOST && h->B <= 1024 && any_nan(z, h->B * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
+  if (memspace == UWVKF_HOST && any_nan(z, h->B * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
   const void *p;
   int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * 16 * sizeof(double), memspace, (void **)&h->d_z, &p);
   if (rc) return rc;
@@ -436,7 +432,7 @@ int uwvkf_velocity_setup_motion_model(uwvkf_handle h, const double *uwv) {
 int uwvkf_velocity_set_gyro(uwvkf_handle h, const double *w, int memspace) {
   REQUIRE(h, UWVKF_FILTER_VELOCITY);
   if (!w) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null input");
-  if (memspace == UWVKF_HOST && h->B <= 1024 && any_nan(w, h->B * 3)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
+  if (memspace == UWVKF_HOST && any_nan(w, h->B * 3)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
   const void *p;
   int rc = stage(h, w, (size_t)h->B * 3 * sizeof(double), (size_t)h->B * 16 * sizeof(double), memspace, (void **)&h->d_z, &p);
   if (rc) return rc;

@@ -2,11 +2,23 @@
 #include "internal.h"
 #include "pose_fused.cuh"
 #include "pose_marker.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace uwvkf {
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+// checkMeasurment() of the reference throws on NaN (src/PoseUKF.cpp:478,494): HOST inputs are scanned for every batch size.
+// Branch-free blocks of 4096 so that the host compiler vectorises the scan (memory bound: ~0.1 ms per million doubles).
+bool any_nan(const double *v, int64_t n) {
+  for (int64_t o = 0; o < n; o += 4096) {
+    const int64_t e = std::min<int64_t>(n, o + 4096);
+    int bad = 0;
+    for (int64_t k = o; k < e; ++k) bad |= (v[k] != v[k]);
+    if (bad) return true;
+  }
+  return false;
+}
 }  // namespace uwvkf
 
 namespace {
@@ -418,14 +430,11 @@ int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, i
   if (!z || !R) return fail(UWVKF_ERR_INVALID_ARGUMENT, "z and R must not be NULL");
   std::memset(&op, 0, sizeof op);
   op.type = 1; op.kind = kind;
-  // checkMeasurment(): NaN in mu or cov throws in the reference.  Host inputs of small batches are checked
-  // here; every input is also checked per filter on the device (UWVKF_ST_NAN_MEASUREMENT).
-  if (memspace == UWVKF_HOST && h->B <= 1024) {
-    for (int64_t k = 0; k < h->B * m; ++k) if (std::isnan(z[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
-  }
+  // checkMeasurment(): NaN in mu or cov throws in the reference.  HOST inputs are scanned here whatever the batch size;
+  // DEVICE inputs cannot be read by the host and are checked per filter in the kernel (UWVKF_ST_NAN_MEASUREMENT).
+  if (memspace == UWVKF_HOST && any_nan(z, h->B * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement contains NaN");
   if (!R_per_filter || memspace == UWVKF_HOST) {
-    int64_t nr = R_per_filter ? h->B * m * m : m * m;
-    if (nr <= 1024 * 9) for (int64_t k = 0; k < nr; ++k) if (std::isnan(R[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement covariance contains NaN");
+    if (any_nan(R, R_per_filter ? h->B * m * m : m * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement covariance contains NaN");
   }
   const void *p;
   int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * pose::MAXM * sizeof(double), memspace, (void **)&h->d_z, &p);
@@ -474,6 +483,7 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (filter_kind != UWVKF_FILTER_POSE) {
     int rc = small_create(h);
+    if (rc == UWVKF_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(UWVKF_ERR_CUDA, "cudaDeviceSynchronize failed after allocation");
     if (rc) { uwvkf_destroy(h); return rc; }
     *out = h;
     return UWVKF_OK;
@@ -496,6 +506,9 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
     uwvkf_destroy(h);
     return fail(UWVKF_ERR_CUDA, "allocation failed: " + msg);
   }
+  // the memsets above ran on the legacy default stream and are asynchronous to the host; user streams (uwvkf_set_stream,
+  // typically cudaStreamNonBlocking) do not order behind it, so they must have finished before the handle is handed out
+  CK(cudaDeviceSynchronize());
   h->pp.mean_tol = h->mean_tol;
   h->pp.mean_max_it = h->mean_max_it;
   *out = h;
@@ -514,6 +527,10 @@ int uwvkf_destroy(uwvkf_handle h) {
 
 int uwvkf_set_stream(uwvkf_handle h, void *s) {
   if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  if (h->capturing) return fail(UWVKF_ERR_INVALID_ARGUMENT, "cannot switch streams during a graph capture");
+  CK(cudaSetDevice(h->device));
+  // staged inputs (d_z, d_tmp, ...) and kernels may still be in flight on the old stream: drain it before the switch
+  CK(cudaStreamSynchronize(h->stream));
   h->stream = (cudaStream_t)s;
   return UWVKF_OK;
 }
@@ -680,8 +697,9 @@ int uwvkf_pose_set_offsets(uwvkf_handle h, const double *offsets, int64_t first,
 int uwvkf_pose_set_rotation_rate(uwvkf_handle h, const double *w, int memspace) {
   REQUIRE(h, UWVKF_FILTER_POSE);
   if (!w) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null rotation rate");
-  if (memspace == UWVKF_HOST && h->B <= 1024)
-    for (int64_t k = 0; k < h->B * 3; ++k) if (std::isnan(w[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "rotation rate contains NaN");
+  // HOST: scanned (the reference throws, src/PoseUKF.cpp:494); DEVICE: the predict kernel refuses a NaN rotation rate per
+  // filter (UWVKF_ST_NAN_MEASUREMENT, prediction skipped)
+  if (memspace == UWVKF_HOST && any_nan(w, h->B * 3)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "rotation rate contains NaN");
   CK(cudaMemcpyAsync(h->d_rot, w, (size_t)h->B * 3 * sizeof(double),
                      memspace == UWVKF_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   return UWVKF_OK;
@@ -750,8 +768,8 @@ int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, cons
   for (int k = 0; k < 7; ++k) { M.marker_pose[k] = marker_pose[k]; M.cam_in_imu[k] = cam_in_imu[k]; }
   for (int k = 0; k < 36; ++k) M.cov_marker[k] = cov_marker[k];
   for (int k = 0; k < 4; ++k) M.camera[k] = camera[k];
-  if (memspace == UWVKF_HOST && h->B <= 1024)   // checkMeasurment() throwing (src/PoseUKF.cpp:635); larger batches: per-filter status bit
-    for (int64_t k = 0; k < h->B * nfeat * 2; ++k) if (std::isnan(px[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "marker corner contains NaN");
+  if (memspace == UWVKF_HOST && any_nan(px, h->B * nfeat * 2))   // checkMeasurment() throwing (src/PoseUKF.cpp:635)
+    return fail(UWVKF_ERR_NAN_MEASUREMENT, "marker corner contains NaN");
   for (int k = 0; k < nfeat * 4; ++k) if (std::isnan(pxcov[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "marker corner covariance contains NaN");
   const double *dpx = px;
   if (memspace == UWVKF_HOST) {
@@ -854,15 +872,15 @@ int uwvkf_stream_push(uwvkf_stream s, double timestamp, int kind, const double *
   } else if (s->have_time && timestamp < s->t_filter) {
     return fail(UWVKF_ERR_INVALID_ARGUMENT, "sample is older than the filter time");
   }
+  // validate everything before the slot is touched: a refused sample leaves the ring as it was (checkMeasurment())
+  const size_t n = (size_t)h->B * m;
+  if (any_nan(z, (int64_t)n)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "sample contains NaN");
+  if (R && any_nan(R, m * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "R contains NaN");
   auto &sl = s->ring[(s->head + s->count) % s->slots];
   if (sl.used) CK(cudaEventSynchronize(sl.copied));   // the staging buffer's previous upload must have left the host
-  const size_t n = (size_t)h->B * m;
-  for (size_t k = 0; k < n; ++k) {
-    if (std::isnan(z[k]) && h->B <= 1024) return fail(UWVKF_ERR_NAN_MEASUREMENT, "sample contains NaN");   // checkMeasurment()
-    sl.h_z[k] = z[k];
-  }
+  std::memcpy(sl.h_z, z, n * sizeof(double));
   sl.ts = timestamp; sl.kind = kind;
-  if (R) for (int k = 0; k < m * m; ++k) { if (std::isnan(R[k])) return fail(UWVKF_ERR_NAN_MEASUREMENT, "R contains NaN"); sl.R[k] = R[k]; }
+  if (R) for (int k = 0; k < m * m; ++k) sl.R[k] = R[k];
   sl.has_aux = aux != nullptr;
   if (aux) {
     const int na = (kind == UWVKF_POSE_WATER_VELOCITY) ? 1 : (kind == UWVKF_POSE_DELAYED_XY ? 2 : 3);

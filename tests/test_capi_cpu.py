@@ -104,3 +104,33 @@ def test_shard_ranges_and_ensemble_reduction_identity(syn):
     assert np.allclose(parts, full, rtol=1e-13)
     n, mean, cov = par.ensemble_mean_cov(full, 54)
     assert n == 100 and np.allclose(mean, mu.mean(0)) and np.allclose(cov, np.cov(mu.T, bias=True), atol=1e-9)
+
+
+def test_converted_temporaries_outlive_the_pointer(pkg):
+    """`_ptr(_f64(list))` used inline in an argument list must not hand out a dangling pointer: the pointer object keeps the
+    converted temporary alive (numpy's small-block cache would otherwise give the next temporary the same address)."""
+    capi = importlib.import_module("slam-uwv_kalman_filters_b200.capi")
+    a, b = capi._ptr(capi._f64([0, 0, 1])), capi._ptr(capi._f64([5, 6, 7]))
+    assert a.value != b.value
+    assert np.array_equal(np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_double)), (3,)), [0, 0, 1])
+    assert np.array_equal(np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_double)), (3,)), [5, 6, 7])
+    c = capi._ptr(capi._f64(np.arange(6, dtype=np.float32).reshape(2, 3)[:, ::2]))      # float32 + non-contiguous -> copy
+    assert np.array_equal(np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_double)), (4,)), [0, 2, 3, 5])
+    assert capi._ptr(None) is None and capi._ptr(1234).value == 1234
+
+
+def test_parity_gates_catch_small_block_errors():
+    """tests/parity.py: the per-component and scaled gates must fail where the global (north_star) metrics are blind."""
+    import parity
+    n = 53
+    sd = np.full(n, 1.0); sd[12:15] = 1e-5            # a gyro-bias-like block
+    cov = np.diag(sd ** 2); cov[20, 20] = 10.0
+    mu = np.zeros(54); mu[6] = 1.0; mu[53] = 1025.0; mu[13:16] = 1e-5
+    bad_mu = mu.copy(); bad_mu[13] *= 1.1             # 10 % error on a 1e-5 bias
+    bad_cov = cov.copy(); bad_cov[12, 12] *= 2.0      # small variance entirely wrong
+    e = parity.all_errs(bad_mu, bad_cov, mu, cov)
+    assert e[0] <= parity.TOL_STATE and e[1] <= parity.TOL_COV            # the global metrics pass ...
+    assert e[2] > 1e-2 and e[3] > 0.5                                     # ... the new gates do not
+    with pytest.raises(AssertionError):
+        parity.check_all(bad_mu[None], bad_cov[None], mu[None], cov[None], "synthetic")
+    assert parity.check_all(mu[None], cov[None], mu[None], cov[None], "identity") == (0.0, 0.0, 0.0, 0.0)

@@ -3,16 +3,13 @@ import numpy as np
 import pytest
 
 import oracle_lib as orc
-from parity import TOL_COV, TOL_STATE, cov_err, state_err
+from parity import check_all
 
 pytestmark = pytest.mark.gpu
 
 
 def check(gmu, gcov, omu, ocov, what):
-    es = max(state_err(gmu[f], omu[f]) for f in range(gmu.shape[0]))
-    ec = max(cov_err(gcov[f], ocov[f]) for f in range(gmu.shape[0]))
-    print(f"[parity] {what}: state {es:.2e} cov {ec:.2e}")
-    assert es <= TOL_STATE and ec <= TOL_COV, (what, es, ec)
+    check_all(gmu, gcov, omu, ocov, what)
 
 
 def test_velocity_ukf_sequence(pkg, syn):
