@@ -373,7 +373,7 @@ def test_lockstep_sequence_parity(pkg, syn, scen):
     step so that the asserted error is the per-step error of north_star."""
     B, STEPS = 8, 40
     ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
-    worst = np.zeros(3)
+    worst = np.zeros(4)
     for s in range(1, STEPS + 1):
         inp = syn.pose_inputs(filt, s)
         w = inp["gyro"]
