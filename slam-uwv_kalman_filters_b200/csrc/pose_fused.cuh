@@ -167,6 +167,28 @@ struct FusedCfg {
 #ifndef UWVKF_TRAIL_PREFETCH_L1   // 1: pull the trailing triangle into L1 instead of L2 at the top of a filter (measured: no gain)
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
+#ifndef UWVKF_ILV                 // 1: trailing pass of the predict+update kernels interleaved with apply_delta (TrailStream)
+#define UWVKF_ILV 1
+#endif
+#ifndef UWVKF_OPAQUE_LANE         // 1: lane index opaque per filter (no loop-invariant hoisting of lane-derived values)
+#define UWVKF_OPAQUE_LANE 0
+#endif
+#ifndef UWVKF_TRAIL_OPAQUE        // 1: lane index opaque inside the trailing passes only
+#define UWVKF_TRAIL_OPAQUE 0
+#endif
+#ifndef UWVKF_COLD_CALL           // 1: the classic trailing pass of the ILV kernels (refused filters only) is an out-of-line call
+#define UWVKF_COLD_CALL 0
+#endif
+#ifndef UWVKF_ILV_UNCLAMPED       // 1: TrailStream addresses rows without the per-column clamp (no lane-dependent column offsets)
+#define UWVKF_ILV_UNCLAMPED 1
+#endif
+#ifndef UWVKF_ILV_EARLY           // 1: request the first batches before the panel downdate instead of after it
+#define UWVKF_ILV_EARLY 0
+#endif
+#ifndef UWVKF_ILV_UB
+#define UWVKF_ILV_UB 8
+#define UWVKF_ILV_DEPTH 2
+#endif
 // Per-phase latency probe (debug builds only, -DUWVKF_PHASE_TIMING; tools/phase_timing.py): warp 0 of every CTA accumulates the
 // clock64() span of each phase of its filters; uwvkf_debug_phase_cycles reads the table.
 #ifdef UWVKF_PHASE_TIMING
@@ -318,15 +340,15 @@ __device__ __forceinline__ double pick6(const double (&v)[6], int i) {
 }
 
 // Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh); T stays in registers.
+// Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh) in three parts, so that a caller can slot
+// independent work between them (apply_delta interleaves batches of the trailing pass): the iterated mean, the deviations with
+// S_oo and A (to shared memory), and T = A Lp^T from the panel-factor rows in registers.
+__device__ __forceinline__ double ori_weight(int p, int K) { return p == 0 ? double(1 + 2 * (N - K)) : (p < 2 * K + 1 ? 1.0 : 0.0); }
 template <int K>
-__device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[K], const double (&a1)[K], const Quat &qp,
-                                                  int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status PH_PARAM) {
-  const bool act = p < 2 * K + 1;
-  const bool on = act && p > 0;
+__device__ __forceinline__ void ori_deviations(double *G, const Quat &qp, const Quat &r, int p, double soo[6]) {
+  const bool on = p > 0 && p < 2 * K + 1;
   const int j = (p - 1) >> 1;
-  const double wa = p == 0 ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
-  Quat r = so3_mean_lane(qp, wa, P.mean_tol, P.mean_max_it, status);
-  PHB(0);
+  const double wa = ori_weight(p, K);
   Vec3 a = so3_boxminus(qp, r);
   const double hw = 0.5 * wa;
   soo[0] = wsum(hw * a.x * a.x);
@@ -341,6 +363,13 @@ __device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[
     G[4 * j + 2] = 0.5 * (a.z - nz);
   }
   __syncwarp();
+}
+template <int K>
+__device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[K], const double (&a1)[K], const Quat &qp,
+                                                  int p, const Params &P, double soo[6], double (&T)[2][3], int lane, unsigned &status PH_PARAM) {
+  Quat r = so3_mean_lane(qp, ori_weight(p, K), P.mean_tol, P.mean_max_it, status);
+  PHB(0);
+  ori_deviations<K>(G, qp, r, p, soo);
   PHB(1);
   PHB(2);
   a_times_panel<K, 3>(G, a0, a1, T);
@@ -486,6 +515,103 @@ __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const dou
   }
 }
 
+// Out-of-line copy for kernels whose common path does not come through here (UWVKF_ILV: only filters whose prediction or update was
+// refused do): as a real call it keeps its column offsets and predicates out of the caller's register allocation.
+template <bool AP, bool AK, int KP, int M, int UB, int DEPTH>
+__device__ __noinline__ void trailing_pass_cold(double *gS, const double *Qs, const double *KC, double f0, double f1, double k00, double k01,
+                                                double k02, double k10, double k11, double k12, double q2add, int lane) {
+  const double f[2] = {f0, f1};
+  const double ks[2][3] = {{k00, k01, k02}, {k10, k11, k12}};
+  trailing_pass<AP, AK, KP, M, UB, DEPTH>(gS, Qs, KC, f, ks, q2add, lane);
+}
+
+// The same pass cut into batches of UB columns that the caller INTERLEAVES with the phases of apply_delta (UWVKF_ILV): the rank-M
+// downdate of the trailing triangle only needs the gain tables (KC, ks), which exist before apply_delta starts, and apply_delta is
+// a chain of dependent, issue-starved phases (a 6-column factorisation, 13 sigma points, an iterated SO3 mean) that touch neither
+// the trailing triangle nor the gain tables.  The loads of a batch are issued before one phase and consumed after it, so their
+// L2 latency (the triangle was prefetched at the top of the filter) hides behind that phase, and the FMAs / stores of the
+// previous batch fill the issue slots the phase leaves empty.  Nothing is stored before the factorisation of apply_delta has
+// succeeded (a failure rolls the update back: the batches in flight are dropped and the classic pass applies the process map only).
+template <bool AP, int KP, int M, int UB, int DEPTH>
+struct TrailStream {
+  static constexpr int NB = (N - KP + UB - 1) / UB;
+  static constexpr int NS = KP <= 20 ? 21 - KP : 0;
+  double v[DEPTH][UB];
+  double vS[NS > 0 ? NS : 1];
+  // Nothing but the values in flight is kept here: the row factors are re-selected from (f, ks) at every use and the column
+  // offsets recomputed from an opaque copy of the lane index (a value the compiler could prove loop invariant would be hoisted
+  // out of the filter loop -- some 90 lane-dependent offsets -- and spilled to local memory, which this kernel serves at L2 latency)
+  __device__ __forceinline__ static double entry(const double *Qs, const double *KC, double q2add, int b, int row, double sv, double fr,
+                                                 double k0, double k1, double k2) {
+    const double2 c01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
+    const double2 c2f = *reinterpret_cast<const double2 *>(KC + 4 * b + 2);
+    if (AP) {
+      sv = fma(fr * c2f.y, sv, Qs[coloff(b) + row]);
+      if (b >= T_WV && b < T_BADCP && row == b) sv += q2add;
+    }
+    sv = fma(-k0, c01.x, sv);
+    if (M > 1) sv = fma(-k1, c01.y, sv);
+    if (M > 2) sv = fma(-k2, c2f.x, sv);
+    return sv;
+  }
+  template <int I> __device__ __forceinline__ void load(const double *gS, int lane) {
+    if constexpr (I < NB) {
+      const int rP = lane <= 20 ? lane + 32 : lane;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int b = KP + I * UB + u;
+#if UWVKF_ILV_UNCLAMPED
+        // rows above the diagonal of column b read a neighbouring entry of the previous column (in range; value dropped)
+        if (b < N) v[I % DEPTH][u] = ldcs_v(gS + rP + coloff(b));
+#else
+        if (b < N) v[I % DEPTH][u] = ldcs_v(gS + coloff(b) + (rP >= b ? rP : b));
+#endif
+      }
+    }
+  }
+  __device__ __forceinline__ void load_secondary(const double *gS, int lane) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lane <= 20 && lane >= KP + u) ? lane : KP + u));
+  }
+  template <int I> __device__ __forceinline__ void finish(bool on, double *gS, const double *Qs, const double *KC, const double (&f)[2],
+                                                          const double (&ks)[2][3], double q2add, int lane) {
+    if constexpr (I < NB) {
+      const bool lo = lane <= 20;
+      const int rP = lo ? lane + 32 : lane;
+      const double fP = lo ? f[1] : f[0];
+      const double kP0 = lo ? ks[1][0] : ks[0][0], kP1 = lo ? ks[1][1] : ks[0][1], kP2 = lo ? ks[1][2] : ks[0][2];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int b = KP + I * UB + u;
+        if (b < N) {
+#if UWVKF_ILV_UNCLAMPED
+          const int rowP = rP;
+#else
+          const int rowP = rP >= b ? rP : b;
+#endif
+#if UWVKF_EXP_NODEP      // experiment: the stored value does not depend on the loaded one (WRONG results; timing only)
+          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, fP, fP, kP0, kP1, kP2));
+#elif UWVKF_EXP_NOSTORE  // experiment: no stores (WRONG results; timing only)
+          if (entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2) == 1.2345e-300) stcs_if(on && rP >= b, gS + coloff(b) + rowP, 0.0);
+#else
+          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2));
+#endif
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void finish_secondary(bool on, double *gS, const double *Qs, const double *KC, const double (&f)[2],
+                                                   const double (&ks)[2][3], double q2add, int lane) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int b = KP + u;
+      const bool actS = lane <= 20 && lane >= b;
+      const int rowS = actS ? lane : b;
+      stcs_if(on && actS, gS + coloff(b) + rowS, entry(Qs, KC, q2add, b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2]));
+    }
+  }
+};
+
 // -1/tau of stored component s (0 when the process model leaves it alone), reference src/PoseUKF.cpp:37-78
 __device__ inline double markov_rate(int s, const Params &P) {
   if (s < P_BG) return 0.0;
@@ -508,7 +634,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   extern __shared__ __align__(16) double smem[];
   double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane_c = threadIdx.x & 31;
+  int lane = lane_c;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *G = w + C::O_G;
   unsigned cur = 0;   // prefix buffer of the current filter (double-buffered builds only)
@@ -568,6 +695,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
     if constexpr (C::DB) { mu = w + cur * C::PBUF; S = mu + C::O_S; }
+#if UWVKF_OPAQUE_LANE
+    // The lane index is made opaque once per filter: everything derived from it inside the loop (row predicates, packed column
+    // offsets, sigma-point signs -- well over a hundred values) would otherwise be proven loop invariant, hoisted out of the
+    // filter loop and, with 168 registers per thread, spilled to local memory, which this kernel serves at L2 latency.
+    // Recomputing them costs integer instructions on a pipe that is 11 % busy.
+    lane = lane_c;
+    asm volatile("" : "+r"(lane));
+#endif
     PH_DECL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -599,7 +734,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     }
     __syncwarp();
     unsigned st = 0;
-    bool predicted = false, updated = false;
+    bool predicted = false, updated = false, trailing_done = false;
+    (void)trailing_done;
     double add = 0.0;
     double ksr[2][3] = {{0, 0, 0}, {0, 0, 0}};   // (K S) rows of the accepted update for the rows this lane owns
 
@@ -948,6 +1084,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
           __syncwarp();
           PH(18);
+          // interleaved trailing pass (TrailStream): the first batches are requested now and fly during the panel downdate and
+          // the factorisation of apply_delta
+          constexpr bool ILV = UWVKF_ILV && HAS_PREDICT;
+          TrailStream<true, KP, M, UWVKF_ILV_UB, UWVKF_ILV_DEPTH> ts;
+          // Filters whose prediction was refused (rare) still run the batches -- no branch around loads whose values are consumed
+          // several phases later -- but with every store predicated off; the classic pass then handles them
+          const bool ilv = ILV && predicted;
+          double *const tgS = blk + OFF_S;
+          const double tq2 = dt2 * add;
+          int tl = lane;
+#if UWVKF_OPAQUE_LANE || UWVKF_TRAIL_OPAQUE
+          asm volatile("" : "+r"(tl));   // opaque per filter (see TrailStream)
+#endif
+          auto ts_step = [&](auto i_) {   // batch I out, batch I + DEPTH in
+            constexpr int I = decltype(i_)::value;
+            ts.template finish<I>(ilv, tgS, Qs, KC, frow, ksr, tq2, tl);
+            ts.template load<I + UWVKF_ILV_DEPTH>(tgS, tl);
+          };
+#if UWVKF_ILV_EARLY
+          if constexpr (ILV) {
+            ts.template load<0>(tgS, tl);
+            if (UWVKF_ILV_DEPTH > 1) ts.template load<1>(tgS, tl);
+            if (UWVKF_ILV_DEPTH > 2) ts.template load<2>(tgS, tl);
+            ts.load_secondary(tgS, tl);
+          }
+#endif
           // panel downdate: Sigma[x][b] -= (KS)_x . K_b
 #pragma unroll
           for (int b = 0; b < KP; ++b) {
@@ -968,6 +1130,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           }
           __syncwarp();
           PH(19);
+#if !UWVKF_ILV_EARLY
+          if constexpr (ILV) {   // the first batches fly during the factorisation of apply_delta
+            ts.template load<0>(tgS, tl);
+            if (UWVKF_ILV_DEPTH > 1) ts.template load<1>(tgS, tl);
+            if (UWVKF_ILV_DEPTH > 2) ts.template load<2>(tgS, tl);
+            ts.load_secondary(tgS, tl);
+          }
+#endif
           // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
           constexpr int KA = 6;
           double c0[KA], c1[KA];
@@ -981,10 +1151,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             const int j = (p - 1) >> 1;
             const double sg = (p & 1) ? 1.0 : -1.0;
             auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<KA> + t] : 0.0; };
+            if constexpr (ILV) { ts.finish_secondary(ilv, tgS, Qs, KC, frow, ksr, tq2, tl); ts_step(std::integral_constant<int, 0>{}); }
             Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
             PH(21);
+            if constexpr (ILV) ts_step(std::integral_constant<int, 1>{});
             double soo[6], TA[2][3];
-            Quat r = ori_transform_reg<KA>(G, c0, c1, qp, p, P, soo, TA, lane, st PH_ARG(22));
+            Quat r = so3_mean_lane(qp, ori_weight(p, KA), P.mean_tol, P.mean_max_it, st);
+            PH(22);
+            if constexpr (ILV) ts_step(std::integral_constant<int, 2>{});
+            ori_deviations<KA>(G, qp, r, p, soo);
+            PH(23);
+            if constexpr (ILV) ts_step(std::integral_constant<int, 3>{});
+            PH(24);
+            a_times_panel<KA, 3>(G, c0, c1, TA);
+            PH(25);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
@@ -1004,6 +1184,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (x1 < N) mu[x1 + 1] += dl[1];
             if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
             updated = true;
+            if constexpr (ILV) {
+              ts_step(std::integral_constant<int, 4>{}); ts_step(std::integral_constant<int, 5>{});
+              ts_step(std::integral_constant<int, 6>{}); ts_step(std::integral_constant<int, 7>{});
+              static_assert(decltype(ts)::NB <= 8, "drain more batches");
+              trailing_done = ilv;
+            }
             __syncwarp();
             PH(26);
           } else {
@@ -1070,14 +1256,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       const double q2add = dt2 * add;
       constexpr int MM_ = (KIND == M_NONE) ? 1 : C::MF::M;
       constexpr int TUB = HAS_PREDICT ? UWVKF_TUB : 8, TDEPTH = HAS_PREDICT ? UWVKF_TDEPTH : 3;
-      if constexpr (KIND == M_NONE) {
-        trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
+      // opaque per filter: the column offsets of the pass are recomputed instead of being hoisted out of the filter loop and
+      // spilled (see TrailStream)
+      int tlane = lane;
+#if UWVKF_OPAQUE_LANE || UWVKF_TRAIL_OPAQUE
+      if (HAS_PREDICT && KIND != M_NONE) asm volatile("" : "+r"(tlane));
+#endif
+#ifndef UWVKF_EXP_SKIPTRAIL
+#define UWVKF_EXP_SKIPTRAIL 0      // experiment: no trailing pass at all (WRONG results; upper bound of what the pass can cost)
+#endif
+      if (trailing_done || UWVKF_EXP_SKIPTRAIL) {
+        // the interleaved pass (TrailStream) has already rewritten the trailing triangle
+      } else if constexpr (KIND == M_NONE) {
+        trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       } else if constexpr (!HAS_PREDICT) {
-        trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
+        trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+      } else if constexpr (UWVKF_ILV && UWVKF_COLD_CALL) {   // rare: the prediction or the update of this filter was refused
+        if (predicted && updated)
+          trailing_pass_cold<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
+        else if (predicted)
+          trailing_pass_cold<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
+        else
+          trailing_pass_cold<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
       } else {
-        if (predicted && updated) trailing_pass<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
-        else if (predicted) trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
-        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, lane);
+        if (predicted && updated) trailing_pass<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        else if (predicted) trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       }
     }
     else {
