@@ -93,6 +93,14 @@ def scenario():
     return syn, cfg, syn.pose_params(cfg), syn.pose_process_noise(cfg, DT)
 
 
+def our_config(filters_per_gpu, world, input_ring=4):
+    """The workload both arms are quoted on (the reference arm times a bounded sample of it)."""
+    return {"workload": "PoseUKF (n=53) fused predictionStep + integrateMeasurement(Velocity), SYNTH-1 inputs",
+            "filters_per_gpu": filters_per_gpu, "filters_total": world * filters_per_gpu, "dt": DT,
+            "parallelism": f"filters sharded x{world}",
+            "l2": "working set 12.5 GB per GPU >> 126 MB L2 (no flush needed)", "input_ring": input_ring}
+
+
 def host_cores():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
     try:
@@ -131,8 +139,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "PoseUKF predict + 3-D DVL update, CPU oracle (literal ukfom recipe, all 107 sigma points)",
-                       "filters_per_step": nf, "dt": DT},
+            "config": our_config(args.filters, args.gpus),
+            "reference_sample": {"what": "CPU oracle = literal ukfom recipe (all 107 sigma points), OpenMP over filters",
+                                 "filters_per_step": nf},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{nf} filters x {args.steps} fused steps, OpenMP over filters"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,47 +202,23 @@ def main():
         g, z = dev_in[i % NR]
         ukf.predict_update(DT, g.data_ptr(), pkg.POSE_VELOCITY, z.data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
 
-    # end-to-end arm: every step uploads that step's gyro + DVL samples from pinned host memory, runs the fused step and
-    # reads the navigation solution (p, q, v) of every filter back to pinned host memory.  The three legs run on three
-    # streams with event dependencies (H2D of step i+1 and D2H of step i-1 overlap the kernel of step i), which is how a
-    # caller streams sensor data through the C ABI: the ABI takes device pointers and is asynchronous on the handle's stream.
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    e2e_in = [(torch.empty((B, 3), dtype=torch.float64, device=dev), torch.empty((B, 3), dtype=torch.float64, device=dev)) for _ in range(2)]
-    e2e_nav = [torch.empty((B, 10), dtype=torch.float64, device=dev) for _ in range(2)]
-    e2e_host = [torch.empty((B, 10), dtype=torch.float64).pin_memory() for _ in range(2)]
-    ev_in, ev_main, ev_out = {}, {}, {}
+    # end-to-end arm: ONE C-ABI call per step with HOST buffers (uwvkf_pose_step_host, include/uwvkf.h): that step's gyro + DVL
+    # samples are read from pinned host memory, the fused step runs, and the navigation solution (p, q, v) of every filter
+    # lands in pinned host memory.  The library pipelines the three legs on its own copy streams (upload of step i+1 and
+    # download of step i-1 overlap the kernel of step i); the host-to-device and device-to-host copies are inside the timed region.
+    host_np = [(g.numpy(), z.numpy()) for g, z in host_in]
+    e2e_host = [torch.empty((B, 10), dtype=torch.float64).pin_memory() for _ in range(3)]
+    e2e_np = [t_.numpy() for t_ in e2e_host]
 
     def step_e2e(i):
-        slot = i % 2
-        with torch.cuda.stream(s_in):
-            if i - 2 in ev_main:
-                s_in.wait_event(ev_main[i - 2])          # the kernel that last read this input slot has finished
-            g, z = host_in[i % NR]
-            e2e_in[slot][0].copy_(g, non_blocking=True)
-            e2e_in[slot][1].copy_(z, non_blocking=True)
-            ev_in[i] = torch.cuda.Event()
-            ev_in[i].record(s_in)
-        with torch.cuda.stream(stream):
-            stream.wait_event(ev_in[i])
-            if i - 2 in ev_out:
-                stream.wait_event(ev_out[i - 2])         # the navigation buffer of this slot has been read back
-            ukf.predict_update(DT, e2e_in[slot][0].data_ptr(), pkg.POSE_VELOCITY, e2e_in[slot][1].data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
-            ukf.get_navigation_into(e2e_nav[slot].data_ptr(), memspace=pkg.DEVICE)
-            ev_main[i] = torch.cuda.Event()
-            ev_main[i].record(stream)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_main[i])
-            e2e_host[slot].copy_(e2e_nav[slot], non_blocking=True)
-            ev_out[i] = torch.cuda.Event()
-            ev_out[i].record(s_out)
-        for d_ in (ev_in, ev_main, ev_out):
-            d_.pop(i - 4, None)
+        g, z = host_np[i % NR]
+        ukf.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL, nav_out=e2e_np[i % 3])
 
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
 
-    def timed(fn, tail_stream=None):
+    def timed(fn, join=False):
         for i in range(W):
             fn(i)
         barrier()
@@ -245,8 +230,8 @@ def main():
             for i in range(K):
                 fn(W + i)
                 ev[i + 1].record(stream)
-            if tail_stream is not None:              # e2e: the timed region ends when the last result has reached the host
-                stream.wait_stream(tail_stream)
+            if join:                                 # e2e: the timed region ends when the last result has reached the host
+                ukf.join()
                 ev[K] = torch.cuda.Event(enable_timing=True)
                 ev[K].record(stream)
         barrier()
@@ -256,7 +241,8 @@ def main():
         return total_ms, per, ukf.kernel_launches - l0, (t0, t1)
 
     tot_ms, per_ms, launches, win = timed(step_resident)
-    e2e_ms, _, e2e_launches, win2 = timed(step_e2e, tail_stream=s_out)
+    e2e_ms, _, e2e_launches, win2 = timed(step_e2e, join=True)
+    assert np.isfinite(e2e_np[(W + K - 1) % 3]).all() and abs(np.linalg.norm(e2e_np[(W + K - 1) % 3][:, 3:7], axis=1) - 1).max() < 1e-9
     st = ukf.get_status()
     faults = int((st != 0).sum())
 
@@ -300,9 +286,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "PoseUKF (n=53) fused predictionStep + integrateMeasurement(Velocity), SYNTH-1 inputs",
-                           "filters_per_gpu": B, "filters_total": world * B, "dt": DT, "parallelism": f"filters sharded x{world}",
-                           "l2": "working set 12.5 GB per GPU >> 126 MB L2 (no flush needed)", "input_ring": NR},
+                "config": our_config(B, world, NR),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "pose_fused_kernel<predict, DVL update, 12 warps>",
                              "traffic_source": traffic_src,
@@ -313,8 +297,9 @@ def main():
                                       "note": "secondary roof; executed flop from the committed ncu capture, peak measured"}},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * 8, "d2h_bytes_per_step": B * 10 * 8,
                         "ms_per_step": e2e_ms / K,
-                        "what": "per step: pinned-host gyro+DVL -> HBM, fused step through the C ABI, navigation solution (p,q,v) of every "
-                                "filter -> pinned host; copies on side streams overlap the neighbouring steps' kernels"},
+                        "what": "per step ONE C-ABI call with HOST buffers (uwvkf_pose_step_host): pinned-host gyro+DVL -> HBM, fused "
+                                "step, navigation solution (p,q,v) of every filter -> pinned host; the library overlaps the copies "
+                                "with the neighbouring steps' kernels"},
                 "gpu_launches": launches, "gpu_launches_e2e": e2e_launches, "clocks": clocks, "filter_faults": faults,
                 "ensemble": {"filters_reduced": n_total, "allreduce_ms": ens_ms}}
         if world == 1 and not args.no_cpu_baseline:

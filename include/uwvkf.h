@@ -173,6 +173,23 @@ int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, cons
 /* Navigation solution of filters [first, first+count): out[count][10] = p(3) q(x,y,z,w) v(3) -- the leading
  * part of getCurrentState() that a caller reads every step.  Asynchronous for memspace == UWVKF_DEVICE. */
 int uwvkf_pose_get_navigation(uwvkf_handle h, double *out, int64_t first, int64_t count, int memspace);
+/* Pipelined HOST-buffer form of the fused hot path: the call a sensor-driver loop makes once per IMU sample.  One call =
+ * integrateMeasurement(RotationRate) + predictionStep(dt) + integrateMeasurement(<kind>) for the whole batch
+ * (src/PoseUKF.cpp:492-496, 446-466, 476-611) followed by a read-back of the navigation solution:
+ *   w_host[B][3], z_host[B][m]  this step's samples in HOST memory (pinned memory makes the copies asynchronous),
+ *   R[m*m], aux                 shared by the batch, as in uwvkf_pose_update,
+ *   nav_out_host[B][10]         (may be NULL) receives p(3) q(x,y,z,w) v(3) of every filter AFTER this step.
+ * The call only enqueues work and returns: uploads run on an internal copy stream into one of two device slots, the fused
+ * kernel on the handle's stream, the download on a second copy stream -- so the upload of step i+1 and the download of step
+ * i-1 overlap the kernel of step i.  Buffer rules: w_host / z_host of call i may be overwritten once call i+1 has returned;
+ * nav_out_host of call i is complete once call i+2 has returned, or after uwvkf_synchronize.  The host never runs more than two
+ * steps ahead of the device.  NaN samples are refused per filter on the device (UWVKF_ST_NAN_MEASUREMENT): a host scan would
+ * serialise the pipeline. */
+int uwvkf_pose_step_host(uwvkf_handle h, double dt, const double *w_host, int meas_kind, const double *z_host, const double *R,
+                         const double *aux, double *nav_out_host);
+/* Orders everything the internal copy streams of uwvkf_pose_step_host still have in flight before whatever is enqueued next on
+ * the handle's stream (so that an event recorded there covers the downloads as well).  uwvkf_synchronize includes it. */
+int uwvkf_join(uwvkf_handle h);
 /* resetFilterWithExternalPose (src/PoseUKF.cpp:685-691): overwrite p and q of every filter, keep Sigma.
  * pose[B][7] = p(3) q(x,y,z,w), host. */
 int uwvkf_pose_reset_with_external_pose(uwvkf_handle h, const double *pose);

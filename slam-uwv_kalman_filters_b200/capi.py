@@ -69,6 +69,8 @@ def load_library():
         lib.uwvkf_pose_update_features.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int]
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
+        lib.uwvkf_pose_step_host.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.uwvkf_join.argtypes = [C.c_void_p]
         lib.uwvkf_ensemble_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_stream_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         lib.uwvkf_stream_destroy.argtypes = [C.c_void_p]
@@ -425,6 +427,19 @@ class PoseUKFBatch(_FilterBatch):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_predict_update(self._h, float(dt), _ptr(w), kind, _ptr(z), _ptr(R), per, _ptr(aux),
                                                      _ptr(valid), memspace))
+
+    def step_host(self, dt, w_host, kind, z_host, R, aux=None, nav_out=None):
+        """Pipelined host-buffer step (uwvkf_pose_step_host): rotation rate + predictionStep(dt) + integrateMeasurement(kind)
+        from HOST sample buffers, navigation solution back into nav_out [B, 10].  Arrays must be C-contiguous float64 (ideally
+        pinned) or raw host addresses; see include/uwvkf.h for when they may be reused."""
+        for a in (w_host, z_host, nav_out):
+            assert a is None or isinstance(a, int) or (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        R, aux = _f64(R), _f64(aux)
+        self._ck(self._lib.uwvkf_pose_step_host(self._h, float(dt), _ptr(w_host), int(kind), _ptr(z_host), _ptr(R), _ptr(aux),
+                                                _ptr(nav_out)))
+
+    def join(self):
+        self._ck(self._lib.uwvkf_join(self._h))
 
     DEBUG_TMERC_SINCOS_LAT, DEBUG_SO3_BOXPLUS, DEBUG_SO3_BOXMINUS, DEBUG_RSQRT, DEBUG_WARP_SUM = range(5)
 

@@ -44,6 +44,14 @@ struct uwvkf_filter_s {
   double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr, *d_uwv = nullptr;
   uwvkf::pose::Params pp{};
   bool have_params = false, have_Q = false;
+  // uwvkf_pose_step_host: two input slots / two navigation buffers, upload and download streams, events per slot
+  struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    double *d_w[2] = {nullptr, nullptr}, *d_z[2] = {nullptr, nullptr}, *d_nav[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool out_pending[2] = {false, false};
+    int64_t calls = 0;
+  } *pipe = nullptr;
   // small filters: state[B][dim + dof*dof], controls, shared process noise
   int dim = 0, dof = 0;
   double Qh[36] = {0};

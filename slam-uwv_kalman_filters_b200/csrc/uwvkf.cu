@@ -520,6 +520,21 @@ int uwvkf_destroy(uwvkf_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
   cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp); cudaFree(h->d_uwv);
+  if (h->pipe) {
+    auto *p = h->pipe;
+    if (p->s_in) cudaStreamSynchronize(p->s_in);
+    if (p->s_out) cudaStreamSynchronize(p->s_out);
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(p->d_w[k]); cudaFree(p->d_z[k]); cudaFree(p->d_nav[k]);
+      if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+      if (p->ev_main[k]) cudaEventDestroy(p->ev_main[k]);
+      if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    delete p;
+    h->pipe = nullptr;
+  }
   small_destroy(h);
   delete h;
   return UWVKF_OK;
@@ -538,6 +553,21 @@ int uwvkf_synchronize(uwvkf_handle h) {
   if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->pipe) {   // downloads of uwvkf_pose_step_host run behind the kernels, on their own stream
+    CK(cudaStreamSynchronize(h->pipe->s_out));
+    h->pipe->out_pending[0] = h->pipe->out_pending[1] = false;
+  }
+  return UWVKF_OK;
+}
+int uwvkf_join(uwvkf_handle h) {
+  if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (h->pipe) {
+    for (int k = 0; k < 2; ++k) {
+      if (h->pipe->out_pending[k]) CK(cudaStreamWaitEvent(h->stream, h->pipe->ev_out[k], 0));
+      if (h->pipe->calls > k) CK(cudaStreamWaitEvent(h->stream, h->pipe->ev_in[k], 0));
+    }
+  }
   return UWVKF_OK;
 }
 int64_t uwvkf_batch(uwvkf_handle h) { return h ? h->B : 0; }
@@ -978,6 +1008,58 @@ int uwvkf_graph_destroy(uwvkf_graph g) {
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   delete g;
+  return UWVKF_OK;
+}
+
+int uwvkf_pose_step_host(uwvkf_handle h, double dt, const double *w_host, int meas_kind, const double *z_host, const double *R,
+                         const double *aux, double *nav_out_host) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  const int m = meas_dim(meas_kind);
+  if (m < 0 || m > 3) return fail(UWVKF_ERR_INVALID_ARGUMENT, "measurement kind not available in the pipelined step");
+  if (!w_host || !z_host || !R || std::isnan(dt)) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null input or NaN dt");
+  if (h->capturing) return fail(UWVKF_ERR_INVALID_ARGUMENT, "host-buffer calls cannot be captured into a graph");
+  if (!h->pipe) {
+    auto *p = new uwvkf_filter_s::HostPipe();
+    h->pipe = p;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaMalloc(&p->d_w[k], (size_t)h->B * 3 * sizeof(double));
+      if (e == cudaSuccess) e = cudaMalloc(&p->d_z[k], (size_t)h->B * 3 * sizeof(double));
+      if (e == cudaSuccess) e = cudaMalloc(&p->d_nav[k], (size_t)h->B * 10 * sizeof(double));
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_main[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return fail(UWVKF_ERR_CUDA, std::string("pipeline allocation failed: ") + cudaGetErrorString(e));
+  }
+  auto *p = h->pipe;
+  const int slot = (int)(p->calls & 1);
+  // host-side pacing (and the buffer rules of the header): the upload of the previous call has left its host buffers, the
+  // download issued two calls ago (same slot) has reached its host buffer
+  if (p->calls >= 1) CK(cudaEventSynchronize(p->ev_in[slot ^ 1]));
+  if (p->out_pending[slot]) { CK(cudaEventSynchronize(p->ev_out[slot])); p->out_pending[slot] = false; }
+  // upload: the slot's previous reader is the kernel of call i-2
+  if (p->calls >= 2) CK(cudaStreamWaitEvent(p->s_in, p->ev_main[slot], 0));
+  CK(cudaMemcpyAsync(p->d_w[slot], w_host, (size_t)h->B * 3 * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+  CK(cudaMemcpyAsync(p->d_z[slot], z_host, (size_t)h->B * m * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+  CK(cudaEventRecord(p->ev_in[slot], p->s_in));
+  // fused step on the handle's stream (the navigation buffer of this slot was read back two calls ago: waited for above)
+  CK(cudaStreamWaitEvent(h->stream, p->ev_in[slot], 0));
+  int rc = uwvkf_pose_predict_update(h, dt, p->d_w[slot], meas_kind, p->d_z[slot], R, 0, aux, nullptr, UWVKF_DEVICE);
+  if (rc) return rc;
+  if (nav_out_host) {
+    rc = uwvkf_pose_get_navigation(h, p->d_nav[slot], 0, h->B, UWVKF_DEVICE);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(p->ev_main[slot], h->stream));
+  if (nav_out_host) {
+    CK(cudaStreamWaitEvent(p->s_out, p->ev_main[slot], 0));
+    CK(cudaMemcpyAsync(nav_out_host, p->d_nav[slot], (size_t)h->B * 10 * sizeof(double), cudaMemcpyDeviceToHost, p->s_out));
+    CK(cudaEventRecord(p->ev_out[slot], p->s_out));
+    p->out_pending[slot] = true;
+  }
+  p->calls++;
   return UWVKF_OK;
 }
 

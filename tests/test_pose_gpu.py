@@ -322,6 +322,43 @@ def test_sample_stream_replays_like_direct_calls(pkg, syn, scen):
     stream.close(); a.close(); b.close()
 
 
+def test_pipelined_host_step_equals_direct_calls(pkg, syn, scen):
+    """uwvkf_pose_step_host (one call per step, HOST sample buffers in, navigation solution out, copies overlapped by the
+    library) gives bit-identical results to rotation rate + predictionStep + integrateMeasurement, and honours its buffer rules."""
+    import torch
+    B, STEPS = 3000, 7
+    a, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    b, *_ = make_batch(pkg, syn, scen, B)
+    ring_in = [(torch.empty((B, 3), dtype=torch.float64).pin_memory().numpy(), torch.empty((B, 3), dtype=torch.float64).pin_memory().numpy())
+               for _ in range(2)]
+    ring_nav = [torch.empty((B, 10), dtype=torch.float64).pin_memory().numpy() for _ in range(3)]
+    expect = []
+    for s in range(1, STEPS + 1):
+        inp = syn.pose_inputs(filt, s)
+        g, z = ring_in[s % 2]                          # inputs of call i may be overwritten once call i+1 has returned
+        g[:] = inp["gyro"]; z[:] = inp["dvl"]
+        a.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL, nav_out=ring_nav[s % 3])
+        b.integrate_rotation_rate(inp["gyro"])
+        b.prediction_step(DT)
+        b.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+        expect.append(b.get_navigation())
+        if s >= 3:                                     # the output of call i is complete once call i+2 has returned
+            assert np.array_equal(ring_nav[(s - 2) % 3], expect[s - 3]), f"navigation output of step {s - 2}"
+    a.synchronize()
+    assert np.array_equal(ring_nav[STEPS % 3], expect[-1]) and np.array_equal(ring_nav[(STEPS - 1) % 3], expect[-2])
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    # NaN samples are refused per filter on the device (the pipelined call does not scan host memory)
+    g, z = ring_in[0]
+    z[5, 1] = np.nan
+    a.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL)
+    a.synchronize()
+    st = a.get_status()
+    assert st[5] & pkg.ST_NAN_MEASUREMENT and np.count_nonzero(st) == 1
+    a.close(); b.close()
+
+
 def test_cuda_graph_replay_of_a_schedule(pkg, syn, scen):
     """A K-step schedule (rotation rate + fused predict/DVL + acceleration per step, inputs resident in HBM) captured once into a
     CUDA graph and replayed == the same calls issued one by one."""
