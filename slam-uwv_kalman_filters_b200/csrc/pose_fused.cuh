@@ -185,6 +185,9 @@ struct FusedCfg {
 #ifndef UWVKF_ILV_EARLY           // 1: request the first batches before the panel downdate instead of after it
 #define UWVKF_ILV_EARLY 0
 #endif
+#ifndef UWVKF_ILV_UPDATE_ONLY     // 1: the update-only kernels interleave their trailing pass as well
+#define UWVKF_ILV_UPDATE_ONLY 1
+#endif
 #ifndef UWVKF_ILV_UB
 #define UWVKF_ILV_UB 8
 #define UWVKF_ILV_DEPTH 2
@@ -1086,11 +1089,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           PH(18);
           // interleaved trailing pass (TrailStream): the first batches are requested now and fly during the panel downdate and
           // the factorisation of apply_delta
-          constexpr bool ILV = UWVKF_ILV && HAS_PREDICT;
-          TrailStream<true, KP, M, UWVKF_ILV_UB, UWVKF_ILV_DEPTH> ts;
+          constexpr bool ILV = UWVKF_ILV && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY);
+          TrailStream<HAS_PREDICT != 0, KP, M, UWVKF_ILV_UB, UWVKF_ILV_DEPTH> ts;
           // Filters whose prediction was refused (rare) still run the batches -- no branch around loads whose values are consumed
           // several phases later -- but with every store predicated off; the classic pass then handles them
-          const bool ilv = ILV && predicted;
+          const bool ilv = ILV && (HAS_PREDICT ? predicted : true);
           double *const tgS = blk + OFF_S;
           const double tq2 = dt2 * add;
           int tl = lane;
@@ -1240,10 +1243,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(mu);
-        // if PANEL is odd the last double2 also carries the (unchanged) first trailing entry: it is rewritten by the
-        // trailing pass below, which is ordered after this copy by the __syncwarp
+        // if PANEL is odd the last double2 would also carry the first trailing entry, which the interleaved trailing pass
+        // has already rewritten in HBM: the last panel entry goes out on its own
+        constexpr int NVW = (C::PANEL & 1) ? NV - 1 : NV;
 #pragma unroll 4
-        for (int k = lane; k < NV; k += 32) __stcs(dst + k, src[k]);
+        for (int k = lane; k < NVW; k += 32) __stcs(dst + k, src[k]);
+        if ((C::PANEL & 1) && lane == 0) __stcs(blk + 2 * NVW, mu[2 * NVW]);
       }
       __syncwarp();
       {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
