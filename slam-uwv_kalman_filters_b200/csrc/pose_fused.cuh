@@ -23,8 +23,8 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
-#ifndef UWVKF_BULK_WB             // 1: panel write-back as one cp.async.bulk (TMA) copy per filter; 2: + second prefix buffer
-#define UWVKF_BULK_WB 0
+#ifndef UWVKF_TWO_BUF             // 1: kernels with a predict keep TWO [mu | panel] buffers per warp (incoming / working): parity green, 1.5 % slower, off
+#define UWVKF_TWO_BUF 0
 #endif
 #ifndef UWVKF_DVL_TAIL            // 1: DVL update as prefix 6 + affine tail (velocity): parity green, 2 % slower than prefix 9
 #define UWVKF_DVL_TAIL 0
@@ -140,17 +140,22 @@ struct FusedCfg {
   // per-warp shared layout (doubles)
   static constexpr int O_MU = 0;                   // 56
   static constexpr int O_S = 56;                   // panel (same indexing as the full packed array)
-  // UWVKF_BULK_WB == 2: a second [mu | panel] buffer, so that the bulk write-back of one filter and the prefix fetch of the
-  // next never touch the same shared memory (only where it still leaves room for 12 warps)
-  static constexpr bool DB = (UWVKF_BULK_WB == 2) && ((PANEL & 1) == 0) && (KP <= 15);
+  // Kernels with a predict keep TWO [mu | panel] buffers per warp: the INCOMING one (O_A), which cp.async fills one filter
+  // ahead, and the WORKING one (O_MU / O_S).  The predict reads the old panel from the first and writes F Sigma F^T + dt^2 Q
+  // into the second, so the panel transform needs no barriers (nothing is updated in place) and the incoming buffer is free --
+  // and refilled with the next filter's prefix -- as soon as the predict is done, a whole update ahead of its use.
+  static constexpr bool TWO = HAS_PREDICT && UWVKF_TWO_BUF && KP <= 15;   // (a 19-column panel twice would cost two warps per SM)
   static constexpr int PBUF = 56 + PANEL_E;        // doubles per prefix buffer
-  static constexpr int O_L = O_S + PANEL_E + (DB ? PBUF : 0);
+  static constexpr int O_A = TWO ? PBUF : 0;       // incoming buffer (the working buffer itself without a predict)
+  static constexpr int O_L = PBUF + (TWO ? PBUF : 0);
   static constexpr int O_G = O_L + LSZ;          // per sigma-point pair j: {A[0][j], A[1][j], A[2][j], -}, AoS [KE][4]
   static constexpr int O_KC = O_G + 4 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
                                                    // 128-bit loads hand a whole warp everything column b contributes)
   static constexpr int O_LT = O_KC + 4 * 54;           // rows T of the panel factor, NT x KE
-  static constexpr int O_IN = O_LT + NT * KE;          // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M)
-  static constexpr int TOTAL = O_IN + 8;
+  // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M); two sets, alternating per filter (the next
+  // filter's inputs arrive while the current filter's update still reads its own)
+  static constexpr int O_IN = O_LT + NT * KE;
+  static constexpr int TOTAL = O_IN + 16;
   // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
@@ -441,6 +446,51 @@ __device__ __forceinline__ void process_panel(double *S, const double *Qs, const
   }
 }
 
+// The same map OUT OF PLACE (kernels with two prefix buffers): old entries are read from SA, new ones written to S.  Nothing is
+// updated in place, so there is no barrier and no staging through registers: every entry is an independent load / FMA / store
+// chain that the scheduler is free to slot between the sigma-point arithmetic that follows.
+template <int KP>
+__device__ __forceinline__ void process_panel_out(const double *SA, double *S, const double *Qs, const double *ftab, const double (&f)[2],
+                                                  double dt, int lane, int colane) {
+  const double dt2 = dt * dt;
+  const bool rp = lane < 3 || (lane >= T_VEL && lane < T_ACC);   // row x0 = lane has a coupled partner (rows x1 never do)
+  const int px = lane + (lane < 3 ? 6 : 3);
+  const int copx = coloff(px);
+  auto group = [&](auto b0_, auto pbo_) {
+    constexpr int b0 = decltype(b0_)::value, pbo = decltype(pbo_)::value;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int b = b0 + i, pb = b + pbo, cb = coloff(b), cpb = coloff(pb);
+      const double fb = ftab[b];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = lane + 32 * h;
+        const int cox = h ? coloff(x < N ? x : 0) : colane;
+        double val = fma(f[h] * fb, SA[cb + x], Qs[cb + x]);
+        val = fma(dt * f[h], SA[x >= pb ? cpb + x : cox + pb], val);
+        if (h == 0) {
+          const double t1 = SA[cb + px], t3 = SA[px >= pb ? cpb + px : copx + pb];
+          val = rp ? fma(dt2, t3, fma(dt * fb, t1, val)) : val;
+        }
+        if (x >= b && x < N && !(x >= 3 && x < 6)) S[cb + x] = val;
+      }
+    }
+  };
+  group(std::integral_constant<int, T_POS>{}, std::integral_constant<int, 6>{});
+  group(std::integral_constant<int, T_VEL>{}, std::integral_constant<int, 3>{});
+#pragma unroll
+  for (int b = T_ACC; b < KP; ++b) {
+    const int cb = coloff(b);
+    const double fb = ftab[b];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x = lane + 32 * h;
+      const double val = fma(f[h] * fb, SA[cb + x], Qs[cb + x]);
+      if (x >= b && x < N) S[cb + x] = val;
+    }
+  }
+}
+
 // Trailing triangle (columns >= KP of the packed covariance, a contiguous suffix of the filter block), streamed HBM -> registers
 // -> HBM once:   s <- f_a f_b s + dt^2 Q_ab - sum_c (K S)_ac K_bc.
 // Rows keep the owner they have everywhere else in the kernel (x0 = lane, x1 = lane + 32), so the row factors f_a, (K S)_a live in
@@ -641,8 +691,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   int lane = lane_c;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *G = w + C::O_G;
-  unsigned cur = 0;   // prefix buffer of the current filter (double-buffered builds only)
-  (void)cur;
+  double *const muA = w + C::O_A, *const SA = muA + C::O_S;   // incoming [mu | panel] (== mu, S without a predict)
+  (void)SA;
+  unsigned par = 0;   // which of the two input sets belongs to the current filter
   double *KC = w + C::O_KC, *LTs = w + C::O_LT;
   (void)LTs;
   {
@@ -673,21 +724,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   const double frow[2] = {ftab[x0], ftab[x1 < N ? x1 : N]};   // affine process factor of the rows this lane owns (1 without predict)
 
   // [mu 54 | pad 2 | panel] is a prefix of the filter block.  It is copied global -> shared asynchronously (cp.async, 16 B per
-  // lane and step, no registers) ONE FILTER AHEAD: the copies for the warp's next filter are issued as soon as the current
-  // panel has been written back, and are waited for at the top of the next iteration, so they fly during the trailing pass.
+  // lane and step, no registers) ONE FILTER AHEAD into the incoming buffer: kernels with a predict issue the copies for the
+  // warp's next filter as soon as the predict has consumed the buffer, the others after the panel has been written back; they
+  // are waited for at the top of the next iteration.
   constexpr int NV = (56 + C::PANEL_E) / 2;
   const unsigned w_saddr = (unsigned)__cvta_generic_to_shared(w);
-  auto fetch_prefix = [&](long long ff, unsigned buf) {
+  auto fetch_prefix = [&](long long ff, unsigned pr) {
     const char *src = reinterpret_cast<const char *>(a.state + ff * BLK);
-    const unsigned dsta = w_saddr + (C::DB ? buf * (8u * C::PBUF) : 0u);
+    const unsigned dsta = w_saddr + 8u * C::O_A;
 #pragma unroll 4
     for (int k = lane; k < NV; k += 32)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta + 16u * k), "l"(src + 16 * k) : "memory");
     // the filter's small inputs ride in the same group, so no global-memory round trip is left inside the iteration
+    const unsigned ina = w_saddr + 8u * (C::O_IN + 8u * pr);
     if (HAS_PREDICT && lane < 3)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(w_saddr + 8u * (C::O_IN + lane)), "l"(a.rot_rate + ff * 3 + lane) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(a.rot_rate + ff * 3 + lane) : "memory");
     if (KIND != M_NONE && lane >= 4 && lane < 4 + C::MF::M)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(w_saddr + 8u * (C::O_IN + lane)), "l"(opu.z + ff * C::MF::M + (lane - 4)) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(opu.z + ff * C::MF::M + (lane - 4)) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   {
@@ -697,7 +750,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
-    if constexpr (C::DB) { mu = w + cur * C::PBUF; S = mu + C::O_S; }
+    const double *const inb = w + C::O_IN + 8 * par;   // this filter's inputs
 #if UWVKF_OPAQUE_LANE
     // The lane index is made opaque once per filter: everything derived from it inside the loop (row predicates, packed column
     // offsets, sigma-point signs -- well over a hundred values) would otherwise be proven loop invariant, hoisted out of the
@@ -745,17 +798,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== predict (k = 15) ====================================================
     if constexpr (HAS_PREDICT) {
       constexpr int K = 15;
-      const double *wm_g = w + C::O_IN;
+      const double *wm_g = inb;
       PH(0);
       double a0[K], a1[K];
       // a NaN rotation rate (device-resident control input the host could not scan) would poison the state: the prediction
       // is refused for this filter (status bit), like checkMeasurment() throwing in the reference (src/PoseUKF.cpp:494)
       const bool wbad = isnan(wm_g[0]) || isnan(wm_g[1]) || isnan(wm_g[2]);
-      const bool spd15 = !wbad && chol_panel<K>(S, Lw, lane, a0, a1);
+      const bool spd15 = !wbad && chol_panel<K>(SA, Lw, lane, a0, a1);
       PH(1);
       if (spd15) {
-        const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
-        const Vec3 vel{mu[P_VEL], mu[P_VEL + 1], mu[P_VEL + 2]};
+        const Quat q{muA[P_ORI], muA[P_ORI + 1], muA[P_ORI + 2], muA[P_ORI + 3]};
+        const Vec3 vel{muA[P_VEL], muA[P_VEL + 1], muA[P_VEL + 2]};
         const int p = lane;
         const bool on = p > 0 && p < 2 * K + 1;
         const int j = (p - 1) >> 1;
@@ -763,9 +816,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<K> + t] : 0.0; };
         Quat qp;
         {
-          double px = mu[P_POS] + d(0), py = mu[P_POS + 1] + d(1);
+          double px = muA[P_POS] + d(0), py = muA[P_POS + 1] + d(1);
           Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
-          Vec3 wb{wm_g[0] - (mu[P_BG] + d(12)), wm_g[1] - (mu[P_BG + 1] + d(13)), wm_g[2] - (mu[P_BG + 2] + d(14))};
+          Vec3 wb{wm_g[0] - (muA[P_BG] + d(12)), wm_g[1] - (muA[P_BG + 1] + d(13)), wm_g[2] - (muA[P_BG + 2] + d(14))};
           double sl, cl;
           tmerc_nav_to_sincos_lat(P.tm, px, py, sl, cl);
           Vec3 wn = qrot(qq, wb);
@@ -798,9 +851,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         // (branch-free: the three cases sit on different lanes of the same warp)
         auto new_mean = [&](int sidx_, double offv) {
           const int sc = sidx_ < DIM ? sidx_ : 0;
-          const double xv = mu[sc];
+          const double xv = muA[sc];
           const bool kin = sc < P_ORI || (sc >= P_VEL && sc < P_ACC);          // position <- velocity, velocity <- acceleration
-          const double partner = mu[kin ? sc + (sc < P_ORI ? P_VEL : 3) : sc];
+          const double partner = muA[kin ? sc + (sc < P_ORI ? P_VEL : 3) : sc];
           const double o = ((sc >= P_INERTIA && sc < P_WV) || sc == P_RHO) ? offv : otab[sc];
           const double rate = kin ? partner : mtau[sc] * (xv - o);
           return fma(dt, rate, xv);
@@ -810,7 +863,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         PH(7);
         // panel <- F panel F^T + dt^2 Q on the affine rows (couplings and scaling in one pass)
         PH(8);
-        process_panel<KP>(S, Qs, ftab, rdf, dt, lane, colane);
+#if !UWVKF_EXP_SKIP_PANEL   // experiment switch (WRONG results; what the phase costs)
+        if constexpr (C::TWO) process_panel_out<KP>(SA, S, Qs, ftab, rdf, dt, lane, colane);
+        else process_panel<KP>(S, Qs, ftab, rdf, dt, lane, colane);
+#endif
         PH(9);
         // orientation rows/cols: T F^T (+ Q cross terms)
 #pragma unroll
@@ -842,6 +898,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         PH(10);
       } else {
         st |= wbad ? ST_NAN_MEAS : ST_NOT_SPD;
+        if constexpr (C::TWO) {   // refused: the working buffer gets the incoming state as it is
+          const double2 *src = reinterpret_cast<const double2 *>(muA);
+          double2 *dst = reinterpret_cast<double2 *>(mu);
+          for (int k = lane; k < NV; k += 32) dst[k] = src[k];
+          __syncwarp();
+        }
+      }
+      if constexpr (C::TWO) {   // the incoming buffer is free: the next filter's prefix lands during the update
+        __syncwarp();
+        const long long fn = f + (long long)gridDim.x * WARPS;
+        if (fn < a.B) fetch_prefix(fn, par ^ 1u);
       }
     }
 
@@ -871,7 +938,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       if (go) {
         bool bad = false;
 #pragma unroll
-        for (int k = 0; k < M; ++k) { z[k] = (w + C::O_IN + 4)[k]; bad |= isnan(z[k]); }
+        for (int k = 0; k < M; ++k) { z[k] = inb[4 + k]; bad |= isnan(z[k]); }
 #pragma unroll
         for (int k = 0; k < M * M; ++k) { Rm[k] = opu.Rdev ? opu.Rdev[f * M * M + k] : opu.R[k]; bad |= isnan(Rm[k]); }
         if (bad) { st |= ST_NAN_MEAS; go = false; }
@@ -1144,7 +1211,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           // ---- apply_delta(K nu): only the orientation (prefix 6) is a manifold component -----------------
           constexpr int KA = 6;
           double c0[KA], c1[KA];
+#if UWVKF_EXP_SKIP_APPLY    // experiment switch (WRONG results; what apply_delta costs)
+          const bool spd6 = false;
+#else
           const bool spd6 = chol_panel<KA>(S, Lw, lane, c0, c1);
+#endif
           PH(20);
           if (spd6) {
             const Quat q{mu[P_ORI], mu[P_ORI + 1], mu[P_ORI + 2], mu[P_ORI + 3]};
@@ -1223,23 +1294,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== write back ===========================================================
     PH(27);
     if (predicted || updated) {
-#if UWVKF_BULK_WB
-      if constexpr ((C::PANEL & 1) == 0) {
-        // [mu | panel] goes back as ONE bulk copy (TMA engine, shared -> global): every lane publishes its shared-memory writes
-        // to the async proxy and lane 0 issues the copy.  With one prefix buffer lane 0 then waits until the engine has READ it
-        // (it is about to be refilled); with two, the next prefix goes to the other buffer, whose own copy -- issued one filter
-        // ago -- is waited for instead (long done).  The writes to HBM finish on their own.
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(blk),
-                       "r"(w_saddr + (C::DB ? cur * (8u * C::PBUF) : 0u)), "r"((unsigned)(NV * 16)) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (C::DB) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-      } else
-#endif
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
         const double2 *src = reinterpret_cast<const double2 *>(mu);
@@ -1251,9 +1305,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if ((C::PANEL & 1) && lane == 0) __stcs(blk + 2 * NVW, mu[2 * NVW]);
       }
       __syncwarp();
-      {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
+      if constexpr (!C::TWO) {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
         const long long fn = f + (long long)gridDim.x * WARPS;
-        if (fn < a.B) fetch_prefix(fn, cur ^ 1u);
+        if (fn < a.B) fetch_prefix(fn, par ^ 1u);
       }
       // trailing triangle (columns >= KP), see trailing_pass: process map and / or rank-M downdate, whichever happened
       PH(28);
@@ -1289,15 +1343,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         else trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       }
     }
-    else {
-#if UWVKF_BULK_WB
-      if (C::DB && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other buffer's copy
-#endif
+    else if constexpr (!C::TWO) {
       __syncwarp();
       const long long fn = f + (long long)gridDim.x * WARPS;
-      if (fn < a.B) fetch_prefix(fn, cur ^ 1u);
+      if (fn < a.B) fetch_prefix(fn, par ^ 1u);
     }
-    if constexpr (C::DB) cur ^= 1u;
+    par ^= 1u;
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();
     PH(29);
@@ -1305,9 +1356,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[39], 1ull);
 #endif
   }
-#if UWVKF_BULK_WB
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every bulk write has landed before the warp exits
-#endif
 }
 
 }  // namespace pose

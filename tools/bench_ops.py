@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--fast-only", action="store_true", help="skip the dense paths (body efforts, visual markers) and the small filters")
+    ap.add_argument("--dense-only", action="store_true", help="only the dense PoseUKF paths (body efforts, visual markers): profiling runs")
     args = ap.parse_args()
     import torch
     pkg = importlib.import_module("slam-uwv_kalman_filters_b200")
@@ -79,14 +80,18 @@ def main():
     for _ in range(3):
         ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
     upd = lambda kind, z, R, aux=None: (lambda: ukf.integrate_measurement(kind, z.data_ptr(), R, aux=aux, memspace=pkg.DEVICE))
-    timeit("pose predict", lambda: ukf.prediction_step(DT), B, P, ukf)
-    timeit("pose update velocity (DVL)", upd(pkg.POSE_VELOCITY, d["dvl"], syn.R_DVL), B, P, ukf)
-    timeit("pose update acceleration", upd(pkg.POSE_ACCELERATION, d["acc"], syn.R_ACC), B, P, ukf)
-    timeit("pose update xy", upd(pkg.POSE_XY, xy, np.eye(2)), B, P, ukf)
-    timeit("pose update z", upd(pkg.POSE_Z, zz, np.eye(1)), B, P, ukf)
-    timeit("pose update pressure", upd(pkg.POSE_PRESSURE, d["pressure"], syn.R_PRESSURE, np.zeros(3)), B, P, ukf)
-    timeit("pose update adcp", upd(pkg.POSE_WATER_VELOCITY, d["adcp"], syn.R_ADCP, np.array([0.5])), B, P, ukf)
-    timeit("pose fused predict+DVL", lambda: ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
+    if args.dense_only:
+        timeit_fast = lambda *a_, **k_: None
+    else:
+        timeit_fast = timeit
+    timeit_fast("pose predict", lambda: ukf.prediction_step(DT), B, P, ukf)
+    timeit_fast("pose update velocity (DVL)", upd(pkg.POSE_VELOCITY, d["dvl"], syn.R_DVL), B, P, ukf)
+    timeit_fast("pose update acceleration", upd(pkg.POSE_ACCELERATION, d["acc"], syn.R_ACC), B, P, ukf)
+    timeit_fast("pose update xy", upd(pkg.POSE_XY, xy, np.eye(2)), B, P, ukf)
+    timeit_fast("pose update z", upd(pkg.POSE_Z, zz, np.eye(1)), B, P, ukf)
+    timeit_fast("pose update pressure", upd(pkg.POSE_PRESSURE, d["pressure"], syn.R_PRESSURE, np.zeros(3)), B, P, ukf)
+    timeit_fast("pose update adcp", upd(pkg.POSE_WATER_VELOCITY, d["adcp"], syn.R_ADCP, np.array([0.5])), B, P, ukf)
+    timeit_fast("pose fused predict+DVL", lambda: ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
                                                                   syn.R_DVL, memspace=pkg.DEVICE), B, P, ukf)
     if args.fast_only:
         if args.out:
@@ -114,6 +119,10 @@ def main():
     faults = int((ukf.get_status() & ~np.uint32(4)).astype(bool).sum())
     res["pose_faults"] = faults
     ukf.close()
+    if args.dense_only:
+        if args.out:
+            json.dump(res, open(args.out, "w"), indent=1)
+        return
 
     # ---------------- small filters
     Bs = args.small_filters

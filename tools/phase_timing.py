@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--lib", default=LIB, help="another build of the library: only ms/step is reported when it has no probes")
+    ap.add_argument("--mean-max-it", type=int, default=0, help="experiment: cap the iterated means (uwvkf_set_mean_policy)")
     ap.add_argument("--define", action="append", default=[], help="extra -D flags for --build (e.g. UWVKF_FUSED_MAX_WARPS=8)")
     args = ap.parse_args()
     if args.build:
@@ -65,6 +66,8 @@ def main():
     cfg = syn.pose_config()
     ukf = pkg.PoseUKFBatch(B, syn.pose_params(cfg), device=0)
     ukf.set_process_noise(syn.pose_process_noise(cfg, DT))
+    if args.mean_max_it:
+        ukf.set_mean_policy(1e-9, args.mean_max_it)
     _, cov0 = syn.pose_initial(cfg)
     CH = 1 << 16
     gy, dv = [], []
