@@ -10,6 +10,7 @@
 // of the centre point and every covariance block becomes an O(n^2) expression in Sigma and the k x k
 // leading Cholesky factor.  tests/test_structured_equivalence.py proves the identity on the CPU.
 #pragma once
+#include <type_traits>
 #include "dmath.cuh"
 
 namespace uwvkf {
@@ -97,8 +98,13 @@ struct WL {
 // ------------------------------------------------------------------------------------------------------
 // Cholesky of the leading K x K block of Sigma.  K <= 32: lane i owns row i in registers, pivots and
 // column entries travel by shuffles (no shared-memory round trips inside the recurrence).
-template <int K>
+// R > K (general path only): the factorisation is carried over R rows -- the first K columns of the factor of the leading
+// R x R block, i.e. the PANEL FACTOR Sigma[0:R, 0:K] L11^-T -- stored column-packed with R rows per column (lidxr<R>).
+template <int R>
+__device__ __forceinline__ int lidxr(int i, int j) { return j * R - ((j * (j - 1)) >> 1) + (i - j); }
+template <int K, int R = K>
 __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double *invd, int lane) {
+  static_assert(R == K || K > 32, "extra rows only in the general path");
   if constexpr (K <= 32) {
     double a[K];
     const int i = lane;
@@ -124,42 +130,74 @@ __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double
     __syncwarp();
     return ok;
   } else {
-    // general path (K up to N): left-looking factorisation, lanes own rows (i = lane + 32 h); column j of L is
-    //   L[i][j] = (Sigma[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j]
-    // with L[j][k] a broadcast load.  One barrier per column and a third of the shared-memory traffic of the right-looking
-    // form (which re-writes the whole trailing block for every column).
-    constexpr int RND = (K + 31) / 32;
+    // general path (K up to N): BLOCKED left-looking factorisation, lanes own rows (i = lane + 32 h).  Four columns jb..jb+3 are
+    // brought up to date together,
+    //   acc[c] = Sigma[i][jb+c] - sum_{k<jb} L[i][k] L[jb+c][k],
+    // so one load of L[i][k] and four broadcast loads of L[jb..jb+3][k] (consecutive in the column-packed factor) feed eight
+    // FMAs on independent accumulators -- the unblocked form spent two loads and three integer instructions per FMA on one
+    // dependent chain (47 % of all instructions of the body-efforts update).  The 4 x 4 diagonal block is then factorised column
+    // by column with the pivots and multipliers travelling by shuffle.  The summation order per entry is the sequential one
+    // (k ascending), so the factor is bit-identical to the unblocked recurrence.
     bool ok = true;
-    for (int j = 0; j < K; ++j) {
-      double sacc[RND];
+    auto block = [&](int jb, auto bw_) {
+      constexpr int BW = decltype(bw_)::value;
+      constexpr int RND = (R + 31) / 32;
+      double acc[RND][BW];
 #pragma unroll
       for (int h = 0; h < RND; ++h) {
         const int i = lane + 32 * h;
-        double acc = 0.0;
-        if (i >= j && i < K) {
-          acc = S[cidx(i, j)];
-          int ei = lidx<K>(i, 0), ej = lidx<K>(j, 0);
-          for (int k = 0; k < j; ++k) {
-            acc = fma(-Lw[ei], Lw[ej], acc);
-            ei += K - k - 1; ej += K - k - 1;          // lidx(i, k + 1) - lidx(i, k)
-          }
+#pragma unroll
+        for (int c = 0; c < BW; ++c) acc[h][c] = (i >= jb + c && i < R) ? S[cidx(i, jb + c)] : 0.0;
+      }
+      // rows above the block (i < jb) have nothing to compute; their lanes run the loop on clamped (in-range) addresses
+      int cb = 0;                       // lidx(0, k) - k: Lw[cb + i] = L[i][k]
+#pragma unroll 2
+      for (int k = 0; k < jb; ++k) {
+        double lj[BW];
+#pragma unroll
+        for (int c = 0; c < BW; ++c) lj[c] = Lw[cb + jb + c];
+#pragma unroll
+        for (int h = 0; h < RND; ++h) {
+          const int i = lane + 32 * h;
+          const double li = Lw[cb + (i >= jb && i < R ? i : jb)];
+#pragma unroll
+          for (int c = 0; c < BW; ++c) acc[h][c] = fma(-li, lj[c], acc[h][c]);
         }
-        sacc[h] = acc;
+        cb += R - k - 1;
       }
-      double dsel = sacc[0];
 #pragma unroll
-      for (int h = 1; h < RND; ++h) if ((j >> 5) == h) dsel = sacc[h];
-      const double d = __shfl_sync(kFull, dsel, j & 31);
-      ok = ok && (d > 0.0);
-      const double inv = rsqrt(d);
+      for (int c = 0; c < BW; ++c) {
+        const int r = jb + c;                                  // pivot row / column
+        double dsel = acc[0][c];
 #pragma unroll
-      for (int h = 0; h < RND; ++h) {
-        const int i = lane + 32 * h;
-        if (i >= j && i < K) Lw[lidx<K>(i, j)] = sacc[h] * inv;
+        for (int h = 1; h < RND; ++h) if ((r >> 5) == h) dsel = acc[h][c];
+        const double d = __shfl_sync(kFull, dsel, r & 31);
+        ok = ok && (d > 0.0);
+        const double inv = rsqrt(d);
+        double lcol[RND];
+#pragma unroll
+        for (int h = 0; h < RND; ++h) {
+          const int i = lane + 32 * h;
+          lcol[h] = acc[h][c] * inv;
+          if (i >= r && i < R) Lw[lidxr<R>(i, r)] = lcol[h];
+        }
+        if (lane == 0) invd[r] = inv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < BW; ++c2) {
+          const int r2 = jb + c2;
+          double lsel = lcol[0];
+#pragma unroll
+          for (int h = 1; h < RND; ++h) if ((r2 >> 5) == h) lsel = lcol[h];
+          const double l2 = __shfl_sync(kFull, lsel, r2 & 31);   // L[r2][r]
+#pragma unroll
+          for (int h = 0; h < RND; ++h) acc[h][c2] = fma(-lcol[h], l2, acc[h][c2]);
+        }
       }
-      if (lane == 0) invd[j] = inv;
       __syncwarp();
-    }
+    };
+    constexpr int NBLK = K / 4, TAIL = K % 4;
+    for (int b = 0; b < NBLK; ++b) block(4 * b, std::integral_constant<int, 4>{});
+    if constexpr (TAIL > 0) block(4 * NBLK, std::integral_constant<int, (TAIL > 0 ? TAIL : 1)>{});
     return ok;
   }
 }
@@ -226,6 +264,37 @@ __device__ __forceinline__ void g_times_sigma(const double *G, int gs, const dou
     }
 #pragma unroll
     for (int r = 0; r < M; ++r) T[r * 56 + x] = acc[r];
+  }
+  __syncwarp();
+}
+
+// T[r][x] = sum_{j<K} Lp[x][j] * B[r][j] for x = 0..N-1, with Lp the panel factor over all N rows (chol_leading<K, N>):
+// Pxz = Sigma[:, :K] L11^-T B^T without the triangular solve G = B L11^-1 and without re-reading Sigma[:K, :].
+template <int K, int M>
+__device__ __forceinline__ void panel_times_b(const double *G, int gs, const double *Lw, double *T, int lane) {
+  double acc[2][M];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int r = 0; r < M; ++r) acc[h][r] = 0.0;
+  const int x1 = lane + 32 < N ? lane + 32 : N - 1;
+  int cb = 0;   // lidxr<N>(0, j) - j
+#pragma unroll 4
+  for (int j = 0; j < K; ++j) {
+    const double l0 = lane >= j ? Lw[cb + lane] : 0.0;     // rows above the diagonal are zeros of the factor
+    const double l1 = x1 >= j ? Lw[cb + x1] : 0.0;
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      const double b = G[r * gs + j];
+      acc[0][r] = fma(b, l0, acc[0][r]);
+      acc[1][r] = fma(b, l1, acc[1][r]);
+    }
+    cb += N - j - 1;
+  }
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+    T[r * 56 + lane] = acc[0][r];
+    if (lane + 32 < N) T[r * 56 + lane + 32] = acc[1][r];
   }
   __syncwarp();
 }
@@ -687,7 +756,11 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
   constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
   double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *G = w + W::G, *T = w + W::T,
          *KS = w + W::KS, *dl = w + W::DL;
-  if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
+  // general path with room for N rows (dense instantiation): carry the factorisation over the whole panel, so that the
+  // cross-covariance is a product with the panel factor (no triangular solve, no G Sigma)
+  constexpr bool PANELF = (K > 32) && (KMAX >= N);
+  constexpr int R = PANELF ? N : K;
+  if (!chol_leading<K, R>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
   // sigma points through the measurement model
   double Z[ROUNDS][M], wt[ROUNDS];
 #pragma unroll
@@ -697,7 +770,7 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
     const bool on = act && p > 0;
     const int j = (p - 1) >> 1;
     const double sg = (p & 1) ? 1.0 : -1.0;
-    auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
+    auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidxr<R>(t, j)] : 0.0; };
     MM::eval(mu, d, aux, P, Z[r], model);
     wt[r] = (p == 0) ? double(1 + 2 * (N - K)) : (act ? 1.0 : 0.0);
   }
@@ -749,8 +822,12 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
     }
   }
   __syncwarp();
-  solve_right<K, M>(G, W::KE, Lw, invd, lane);
-  g_times_sigma<K, M>(G, W::KE, S, T, lane);
+  if constexpr (PANELF) {
+    panel_times_b<K, M>(G, W::KE, Lw, T, lane);
+  } else {
+    solve_right<K, M>(G, W::KE, Lw, invd, lane);
+    g_times_sigma<K, M>(G, W::KE, S, T, lane);
+  }
   // gain, innovation, gate
   double Si[M * M];
   sym_inverse<M>(Szz, Si);
