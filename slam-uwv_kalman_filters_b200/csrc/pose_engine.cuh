@@ -82,7 +82,9 @@ __device__ __forceinline__ int sidx(int a, int b) { return a >= b ? cidx(a, b) :
 // per-warp shared-memory layout (doubles)
 template <int KMAX>
 struct WL {
-  static constexpr int MG = KMAX >= 48 ? MAXM : 3;                  // rows of G / T / KS (max measurement dim)
+  // rows of G / T / KS (max measurement dim): six for the dense instantiation and for KMAX == 20, the prefix-19 engine with
+  // room for the six-dimensional velocity-only body-efforts update (prefix 9)
+  static constexpr int MG = (KMAX >= 48 || KMAX == 20) ? MAXM : 3;
   static constexpr int LSZ = ((KMAX * (KMAX + 1) / 2 + 1) / 2) * 2;
   static constexpr int KE = ((KMAX + 1) / 2) * 2;
   static constexpr int L = BLK;             // leading-block Cholesky factor, packed by columns (dimension K)
@@ -314,9 +316,9 @@ __device__ __forceinline__ Quat so3_mean(const Quat (&qp)[ROUNDS], const double 
       Vec3 d = so3_boxminus(qp[k], r);
       mx = fma(wt[k], d.x, mx); my = fma(wt[k], d.y, my); mz = fma(wt[k], d.z, mz);
     }
-    mx = warp_sum(mx) / double(2 * N + 1);
-    my = warp_sum(my) / double(2 * N + 1);
-    mz = warp_sum(mz) / double(2 * N + 1);
+    mx = wsum(mx) / double(2 * N + 1);
+    my = wsum(my) / double(2 * N + 1);
+    mz = wsum(mz) / double(2 * N + 1);
     r = so3_boxplus(r, Vec3{mx, my, mz}, 1.0);
     nrm = sqrt(mx * mx + my * my + mz * mz);
   } while (nrm > tol && ++it < max_it);
@@ -339,12 +341,12 @@ __device__ __forceinline__ Quat ori_transform(double *w, const Quat &qp, int p, 
   Quat r = so3_mean<1>(qa, wa, P.mean_tol, P.mean_max_it, status);
   Vec3 a = so3_boxminus(qp, r);
   const double hw = 0.5 * wa[0];
-  soo[0] = warp_sum(hw * a.x * a.x);
-  soo[1] = warp_sum(hw * a.y * a.x);
-  soo[2] = warp_sum(hw * a.z * a.x);
-  soo[3] = warp_sum(hw * a.y * a.y);
-  soo[4] = warp_sum(hw * a.z * a.y);
-  soo[5] = warp_sum(hw * a.z * a.z);
+  soo[0] = wsum(hw * a.x * a.x);
+  soo[1] = wsum(hw * a.y * a.x);
+  soo[2] = wsum(hw * a.z * a.x);
+  soo[3] = wsum(hw * a.y * a.y);
+  soo[4] = wsum(hw * a.z * a.y);
+  soo[5] = wsum(hw * a.z * a.z);
   // A_j = 1/2 (a_{2j+1} - a_{2j+2}): odd lanes pair with lane + 1
   double nx = __shfl_down_sync(kFull, a.x, 1), ny = __shfl_down_sync(kFull, a.y, 1), nz = __shfl_down_sync(kFull, a.z, 1);
   if (on && (p & 1)) {
@@ -704,37 +706,54 @@ __device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
     double id = 1.0 / (S[0] * S[3] - S[1] * S[2]);
     Si[0] = S[3] * id; Si[1] = -S[1] * id; Si[2] = -S[2] * id; Si[3] = S[0] * id;
   } else if constexpr (M > 3) {
-    // Gauss-Jordan with partial pivoting (what Eigen's fixed-size inverse does above 4x4, as SURVEY.md Appendix B.2 describes)
-    double a[M * M];
+    // Gauss-Jordan with partial pivoting (what Eigen's fixed-size inverse does above 4x4, as SURVEY.md Appendix B.2 describes),
+    // one COLUMN of the augmented matrix [S | I] per lane (lanes 0 .. 2M-1): row operations act on every column independently,
+    // the pivot column travels by shuffle, and nothing is indexed at run time.  (Every lane eliminating its own copy of the
+    // 2 x M x M entries needs 144 registers for M = 6 and a run-time pivot index: the arrays went to local memory -- a quarter
+    // of the stall samples of the body-efforts kernels.)  Same operations in the same order per entry as the sequential form.
+    const int lane_ = threadIdx.x & 31;
+    double col[M];
 #pragma unroll
-    for (int i = 0; i < M * M; ++i) { a[i] = S[i]; Si[i] = (i / M == i % M) ? 1.0 : 0.0; }
+    for (int r = 0; r < M; ++r) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < M; ++k) v = (lane_ == k) ? S[r * M + k] : v;
+      col[r] = (lane_ == M + r) ? 1.0 : v;
+    }
 #pragma unroll
     for (int c = 0; c < M; ++c) {
-      int p = c;
+      double cc[M];
 #pragma unroll
-      for (int r = c + 1; r < M; ++r) if (fabs(a[r * M + c]) > fabs(a[p * M + c])) p = r;
+      for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(kFull, col[r], c);
+      int p = c;
+      double best = fabs(cc[c]);
 #pragma unroll
       for (int r = c + 1; r < M; ++r) {
-        if (r == p) {
-#pragma unroll
-          for (int k = 0; k < M; ++k) {
-            double t = a[r * M + k]; a[r * M + k] = a[c * M + k]; a[c * M + k] = t;
-            t = Si[r * M + k]; Si[r * M + k] = Si[c * M + k]; Si[c * M + k] = t;
-          }
-        }
+        const double v = fabs(cc[r]);
+        if (v > best) { best = v; p = r; }
       }
-      const double ip = 1.0 / a[c * M + c];
 #pragma unroll
-      for (int k = 0; k < M; ++k) { a[c * M + k] *= ip; Si[c * M + k] *= ip; }
+      for (int r = c + 1; r < M; ++r) {
+        const bool sw = (r == p);
+        const double t = col[r], u = cc[r];
+        col[r] = sw ? col[c] : col[r]; col[c] = sw ? t : col[c];
+        cc[r] = sw ? cc[c] : cc[r]; cc[c] = sw ? u : cc[c];
+      }
+      const double ip = 1.0 / cc[c];
+      col[c] *= ip;
 #pragma unroll
       for (int r = 0; r < M; ++r) {
         if (r != c) {
-          const double f = a[r * M + c];
-#pragma unroll
-          for (int k = 0; k < M; ++k) { a[r * M + k] -= f * a[c * M + k]; Si[r * M + k] -= f * Si[c * M + k]; }
+          const double f = cc[r];
+          col[r] -= f * col[c];
         }
       }
     }
+    // lanes M .. 2M-1 hold the columns of the inverse: hand every lane the whole matrix
+#pragma unroll
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+      for (int k = 0; k < M; ++k) Si[r * M + k] = __shfl_sync(kFull, col[r], M + k);
   } else {
     double c00 = S[4] * S[8] - S[5] * S[7], c01 = S[5] * S[6] - S[3] * S[8], c02 = S[3] * S[7] - S[4] * S[6];
     double id = 1.0 / (S[0] * c00 + S[1] * c01 + S[2] * c02);
@@ -788,7 +807,7 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
         double m = 0;
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) m = fma(wt[r], Z[r][a] - zb[a], m);
-        m = warp_sum(m) / double(2 * N + 1);
+        m = wsum(m) / double(2 * N + 1);
         zb[a] += m;
         nrm += m * m;
       }
@@ -805,7 +824,7 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
       double s = 0;
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) s = fma(0.5 * wt[r] * (Z[r][a] - zb[a]), Z[r][b] - zb[b], s);
-      s = warp_sum(s);
+      s = wsum(s);
       Szz[a * M + b] = s + Rm[a * M + b];
       Szz[b * M + a] = s + Rm[b * M + a];
     }

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a
       const int kind = op.kind;
       const bool efforts = (kind == pose::M_BODY_EFFORTS || kind == pose::M_BODY_EFFORTS_VELOCITY_ONLY);
       const int m = efforts ? 6 : ((kind == pose::M_Z || kind == pose::M_PRESSURE) ? 1 : ((kind == pose::M_VELOCITY || kind == pose::M_ACCELERATION) ? 3 : 2));
-      constexpr int MZ = KMAX >= 48 ? pose::MAXM : 3;
+      constexpr int MZ = (KMAX >= 48 || KMAX == 20) ? pose::MAXM : 3;
       double z[MZ], R[MZ * MZ];
       bool bad = false;
       if (m > MZ) continue;   // six-dimensional measurements are routed to the dense instantiation by the host
@@ -88,6 +88,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a
           break;
         }
         default:
+          if constexpr (KMAX == 20) {   // constrainVelocity (reference src/PoseUKF.cpp:198-219, 585-592): prefix 9, m = 6
+            if (kind == pose::M_BODY_EFFORTS_VELOCITY_ONLY) {
+              double *ctx = w + W::F;
+              pose::efforts_context(w, a.rot_rate + f * 3, P, ctx);
+              __syncwarp();
+              dirty |= pose::update<pose::M_BODY_EFFORTS_VELOCITY_ONLY, KMAX>(w, lut, z, R, ctx, false, P, lane, st, a.uwv);
+            }
+          }
           if constexpr (KMAX >= 53) {
             if (kind == pose::M_PRESSURE) dirty |= pose::update<pose::M_PRESSURE, KMAX>(w, lut, z, R, op.aux, false, P, lane, st);
             else if (kind == pose::M_WATER_VELOCITY) dirty |= pose::update<pose::M_WATER_VELOCITY, KMAX>(w, lut, z, R, op.aux, true, P, lane, st);
@@ -265,7 +273,7 @@ namespace {
 #ifndef UWVKF_UPDATE_WARPS
 #define UWVKF_UPDATE_WARPS UWVKF_FUSED_MAX_WARPS
 #endif
-constexpr int kFastWarps = 12, kSlowWarps = 6, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS, kUpdateMaxWarps = UWVKF_UPDATE_WARPS;
+constexpr int kFastWarps = 12, kSlowWarps = 6, kEffortsVelWarps = 10, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS, kUpdateMaxWarps = UWVKF_UPDATE_WARPS;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
 }  // namespace
@@ -387,7 +395,7 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   L.state = h->d_state; L.offsets = h->d_offsets; L.rot_rate = h->d_rot; L.status = h->d_status; L.Q = h->d_Q;
   L.uwv = h->d_uwv;
   L.B = h->B; L.nops = nops;
-  bool slow = false, dense_only = false;
+  bool slow = false, dense_only = false, full_efforts = false;
   for (int o = 0; o < nops; ++o) {
     L.ops[o] = ops[o];
     if (ops[o].type == 0 && !h->have_Q) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_set_process_noise was not called");
@@ -395,6 +403,7 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
     if (ops[o].type == 1 && (ops[o].kind == UWVKF_POSE_BODY_EFFORTS || ops[o].kind == UWVKF_POSE_BODY_EFFORTS_VELOCITY_ONLY)) {
       if (!h->d_uwv) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_model_parameters was not called");
       slow = dense_only = true;
+      full_efforts |= ops[o].kind == UWVKF_POSE_BODY_EFFORTS;
     }
   }
   // engine selection: "panel + stream" kernel for predict / update / predict+update (pressure and ADCP through their
@@ -406,6 +415,8 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
     if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
     if (nops == 2 && ops[0].type == 0 && ops[1].type == 1) return launch_fused_kind<1>(h, L, ops[1].kind);
   }
+  // the velocity-only body-efforts update reads prefix 9 only: prefix-19 engine with six-row tables, 10 warps per SM
+  if (!force_v1 && dense_only && !full_efforts && nops == 1) return launch_pose<20, kEffortsVelWarps>(h, L);
   return slow ? launch_pose<53, kSlowWarps>(h, L) : launch_pose<19, kFastWarps>(h, L);
 }
 
