@@ -98,12 +98,87 @@ struct WL {
 };
 
 // ------------------------------------------------------------------------------------------------------
+// entry (i, j), i >= j, of a lower triangle packed by columns with R rows per column
+template <int R>
+__device__ __forceinline__ int lidxr(int i, int j) { return j * R - ((j * (j - 1)) >> 1) + (i - j); }
+// BLOCKED left-looking Cholesky of the leading K columns of a column-packed symmetric matrix (SN rows per column), carried over
+// R >= K rows (R > K: the panel factor of the leading R x K block); lanes own rows (i = lane + 32 h).  Four columns jb..jb+3 are
+// brought up to date together,
+//   acc[c] = S[i][jb+c] - sum_{k<jb} L[i][k] L[jb+c][k],
+// so one load of L[i][k] and four broadcast loads of L[jb..jb+3][k] (consecutive in the column-packed factor) feed eight FMAs on
+// independent accumulators -- the unblocked form spent two loads and three integer instructions per FMA on one dependent chain
+// (47 % of all instructions of the body-efforts update, 70 % of the visual-marker update).  The 4 x 4 diagonal block is then
+// factorised column by column with the pivots and multipliers travelling by shuffle.  The summation order per entry is the
+// sequential one (k ascending).  The factor is stored column-packed with R rows per column (lidxr<R>).
+template <int K, int R, int SN, bool FAST>
+__device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double *invd, int lane) {
+  bool ok = true;
+  auto block = [&](int jb, auto bw_) {
+    constexpr int BW = decltype(bw_)::value;
+    constexpr int RND = (R + 31) / 32;
+    double acc[RND][BW];
+#pragma unroll
+    for (int h = 0; h < RND; ++h) {
+      const int i = lane + 32 * h;
+#pragma unroll
+      for (int c = 0; c < BW; ++c) acc[h][c] = (i >= jb + c && i < R) ? S[lidxr<SN>(i, jb + c)] : 0.0;
+    }
+    // rows above the block (i < jb) have nothing to compute; their lanes run the loop on clamped (in-range) addresses
+    int cb = 0;                       // lidx(0, k) - k: Lw[cb + i] = L[i][k]
+#pragma unroll 2
+    for (int k = 0; k < jb; ++k) {
+      double lj[BW];
+#pragma unroll
+      for (int c = 0; c < BW; ++c) lj[c] = Lw[cb + jb + c];
+#pragma unroll
+      for (int h = 0; h < RND; ++h) {
+        const int i = lane + 32 * h;
+        const double li = Lw[cb + (i >= jb && i < R ? i : jb)];
+#pragma unroll
+        for (int c = 0; c < BW; ++c) acc[h][c] = fma(-li, lj[c], acc[h][c]);
+      }
+      cb += R - k - 1;
+    }
+#pragma unroll
+    for (int c = 0; c < BW; ++c) {
+      const int r = jb + c;                                  // pivot row / column
+      double dsel = acc[0][c];
+#pragma unroll
+      for (int h = 1; h < RND; ++h) if ((r >> 5) == h) dsel = acc[h][c];
+      const double d = __shfl_sync(kFull, dsel, r & 31);
+      ok = ok && (d > 0.0);
+      const double inv = FAST ? fast_rsqrt3(d) : rsqrt(d);
+      double lcol[RND];
+#pragma unroll
+      for (int h = 0; h < RND; ++h) {
+        const int i = lane + 32 * h;
+        lcol[h] = acc[h][c] * inv;
+        if (i >= r && i < R) Lw[lidxr<R>(i, r)] = lcol[h];
+      }
+      if (invd != nullptr && lane == 0) invd[r] = inv;
+#pragma unroll
+      for (int c2 = c + 1; c2 < BW; ++c2) {
+        const int r2 = jb + c2;
+        double lsel = lcol[0];
+#pragma unroll
+        for (int h = 1; h < RND; ++h) if ((r2 >> 5) == h) lsel = lcol[h];
+        const double l2 = __shfl_sync(kFull, lsel, r2 & 31);   // L[r2][r]
+#pragma unroll
+        for (int h = 0; h < RND; ++h) acc[h][c2] = fma(-lcol[h], l2, acc[h][c2]);
+      }
+    }
+    __syncwarp();
+  };
+  constexpr int NBLK = K / 4, TAIL = K % 4;
+  for (int b = 0; b < NBLK; ++b) block(4 * b, std::integral_constant<int, 4>{});
+  if constexpr (TAIL > 0) block(4 * NBLK, std::integral_constant<int, (TAIL > 0 ? TAIL : 1)>{});
+  return ok;
+}
+
 // Cholesky of the leading K x K block of Sigma.  K <= 32: lane i owns row i in registers, pivots and
 // column entries travel by shuffles (no shared-memory round trips inside the recurrence).
 // R > K (general path only): the factorisation is carried over R rows -- the first K columns of the factor of the leading
 // R x R block, i.e. the PANEL FACTOR Sigma[0:R, 0:K] L11^-T -- stored column-packed with R rows per column (lidxr<R>).
-template <int R>
-__device__ __forceinline__ int lidxr(int i, int j) { return j * R - ((j * (j - 1)) >> 1) + (i - j); }
 template <int K, int R = K>
 __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double *invd, int lane) {
   static_assert(R == K || K > 32, "extra rows only in the general path");
@@ -132,75 +207,8 @@ __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double
     __syncwarp();
     return ok;
   } else {
-    // general path (K up to N): BLOCKED left-looking factorisation, lanes own rows (i = lane + 32 h).  Four columns jb..jb+3 are
-    // brought up to date together,
-    //   acc[c] = Sigma[i][jb+c] - sum_{k<jb} L[i][k] L[jb+c][k],
-    // so one load of L[i][k] and four broadcast loads of L[jb..jb+3][k] (consecutive in the column-packed factor) feed eight
-    // FMAs on independent accumulators -- the unblocked form spent two loads and three integer instructions per FMA on one
-    // dependent chain (47 % of all instructions of the body-efforts update).  The 4 x 4 diagonal block is then factorised column
-    // by column with the pivots and multipliers travelling by shuffle.  The summation order per entry is the sequential one
-    // (k ascending), so the factor is bit-identical to the unblocked recurrence.
-    bool ok = true;
-    auto block = [&](int jb, auto bw_) {
-      constexpr int BW = decltype(bw_)::value;
-      constexpr int RND = (R + 31) / 32;
-      double acc[RND][BW];
-#pragma unroll
-      for (int h = 0; h < RND; ++h) {
-        const int i = lane + 32 * h;
-#pragma unroll
-        for (int c = 0; c < BW; ++c) acc[h][c] = (i >= jb + c && i < R) ? S[cidx(i, jb + c)] : 0.0;
-      }
-      // rows above the block (i < jb) have nothing to compute; their lanes run the loop on clamped (in-range) addresses
-      int cb = 0;                       // lidx(0, k) - k: Lw[cb + i] = L[i][k]
-#pragma unroll 2
-      for (int k = 0; k < jb; ++k) {
-        double lj[BW];
-#pragma unroll
-        for (int c = 0; c < BW; ++c) lj[c] = Lw[cb + jb + c];
-#pragma unroll
-        for (int h = 0; h < RND; ++h) {
-          const int i = lane + 32 * h;
-          const double li = Lw[cb + (i >= jb && i < R ? i : jb)];
-#pragma unroll
-          for (int c = 0; c < BW; ++c) acc[h][c] = fma(-li, lj[c], acc[h][c]);
-        }
-        cb += R - k - 1;
-      }
-#pragma unroll
-      for (int c = 0; c < BW; ++c) {
-        const int r = jb + c;                                  // pivot row / column
-        double dsel = acc[0][c];
-#pragma unroll
-        for (int h = 1; h < RND; ++h) if ((r >> 5) == h) dsel = acc[h][c];
-        const double d = __shfl_sync(kFull, dsel, r & 31);
-        ok = ok && (d > 0.0);
-        const double inv = rsqrt(d);
-        double lcol[RND];
-#pragma unroll
-        for (int h = 0; h < RND; ++h) {
-          const int i = lane + 32 * h;
-          lcol[h] = acc[h][c] * inv;
-          if (i >= r && i < R) Lw[lidxr<R>(i, r)] = lcol[h];
-        }
-        if (lane == 0) invd[r] = inv;
-#pragma unroll
-        for (int c2 = c + 1; c2 < BW; ++c2) {
-          const int r2 = jb + c2;
-          double lsel = lcol[0];
-#pragma unroll
-          for (int h = 1; h < RND; ++h) if ((r2 >> 5) == h) lsel = lcol[h];
-          const double l2 = __shfl_sync(kFull, lsel, r2 & 31);   // L[r2][r]
-#pragma unroll
-          for (int h = 0; h < RND; ++h) acc[h][c2] = fma(-lcol[h], l2, acc[h][c2]);
-        }
-      }
-      __syncwarp();
-    };
-    constexpr int NBLK = K / 4, TAIL = K % 4;
-    for (int b = 0; b < NBLK; ++b) block(4 * b, std::integral_constant<int, 4>{});
-    if constexpr (TAIL > 0) block(4 * NBLK, std::integral_constant<int, (TAIL > 0 ? TAIL : 1)>{});
-    return ok;
+    // general path (K up to N): blocked left-looking factorisation, lanes own rows (chol_blocked)
+    return chol_blocked<K, R, N, false>(S, Lw, invd, lane);
   }
 }
 

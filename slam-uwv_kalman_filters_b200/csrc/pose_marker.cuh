@@ -46,42 +46,9 @@ struct MarkerLayout {              // per-warp shared memory (doubles)
   static constexpr int TOTAL = O_DL + 60;
 };
 
-// left-looking Cholesky of the packed NA x NA matrix A into L (both in shared memory)
+// Cholesky of the packed NA x NA matrix A into L (both in shared memory): blocked left-looking (chol_blocked, pose_engine.cuh)
 __device__ __forceinline__ bool chol_aug(const double *A, double *L, int lane) {
-  bool ok = true;
-  for (int j = 0; j < NA; ++j) {
-    double s[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = lane + 32 * h;
-      double acc = 0.0;
-      if (i >= j && i < NA) {
-        acc = A[aidx(i, j)];
-        int ei = i, ej = j;                              // aidx(i, 0), aidx(j, 0); aidx(., k + 1) - aidx(., k) = NA - k - 1
-        double acc2 = 0.0;                               // two partial sums: half the dependent depth
-        int k = 0;
-        for (; k + 1 < j; k += 2) {
-          acc = fma(-L[ei], L[ej], acc);
-          const int st1 = NA - k - 1;
-          acc2 = fma(-L[ei + st1], L[ej + st1], acc2);
-          ei += 2 * NA - 2 * k - 3; ej += 2 * NA - 2 * k - 3;
-        }
-        if (k < j) acc = fma(-L[ei], L[ej], acc);
-        acc += acc2;
-      }
-      s[h] = acc;
-    }
-    const double d = __shfl_sync(kFull, (j < 32) ? s[0] : s[1], j & 31);
-    ok = ok && (d > 0.0);
-    const double inv = fast_rsqrt3(d);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = lane + 32 * h;
-      if (i >= j && i < NA) L[aidx(i, j)] = s[h] * inv;
-    }
-    __syncwarp();
-  }
-  return ok;
+  return chol_blocked<NA, NA, NA, true>(A, L, nullptr, lane);
 }
 
 template <int WARPS>
