@@ -113,18 +113,19 @@ __device__ __forceinline__ int lidxr(int i, int j) { return j * R - ((j * (j - 1
 template <int K, int R, int SN, bool FAST>
 __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double *invd, int lane) {
   bool ok = true;
-  auto block = [&](int jb, auto bw_) {
-    constexpr int BW = decltype(bw_)::value;
-    constexpr int RND = (R + 31) / 32;
+  // Rows are dealt out RELATIVE to the block: lane l works on rows jb + l (and jb + l + 32 while the block still has more than 32
+  // rows below its top), so no lane idles on rows above the block, the second round disappears for the later blocks, and the
+  // pivot row jb + c always sits on lane c.
+  auto block = [&](int jb, auto bw_, auto rnd_) {
+    constexpr int BW = decltype(bw_)::value, RND = decltype(rnd_)::value;
     double acc[RND][BW];
 #pragma unroll
     for (int h = 0; h < RND; ++h) {
-      const int i = lane + 32 * h;
+      const int i = jb + lane + 32 * h;
 #pragma unroll
       for (int c = 0; c < BW; ++c) acc[h][c] = (i >= jb + c && i < R) ? S[lidxr<SN>(i, jb + c)] : 0.0;
     }
-    // rows above the block (i < jb) have nothing to compute; their lanes run the loop on clamped (in-range) addresses
-    int cb = 0;                       // lidx(0, k) - k: Lw[cb + i] = L[i][k]
+    int cb = 0;                       // lidxr<R>(0, k) - k: Lw[cb + i] = L[i][k]
 #pragma unroll 2
     for (int k = 0; k < jb; ++k) {
       double lj[BW];
@@ -132,8 +133,8 @@ __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double
       for (int c = 0; c < BW; ++c) lj[c] = Lw[cb + jb + c];
 #pragma unroll
       for (int h = 0; h < RND; ++h) {
-        const int i = lane + 32 * h;
-        const double li = Lw[cb + (i >= jb && i < R ? i : jb)];
+        const int i = jb + lane + 32 * h;
+        const double li = Lw[cb + (i < R ? i : jb)];     // lanes past the last row run on a clamped (in-range) address
 #pragma unroll
         for (int c = 0; c < BW; ++c) acc[h][c] = fma(-li, lj[c], acc[h][c]);
       }
@@ -141,28 +142,21 @@ __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double
     }
 #pragma unroll
     for (int c = 0; c < BW; ++c) {
-      const int r = jb + c;                                  // pivot row / column
-      double dsel = acc[0][c];
-#pragma unroll
-      for (int h = 1; h < RND; ++h) if ((r >> 5) == h) dsel = acc[h][c];
-      const double d = __shfl_sync(kFull, dsel, r & 31);
+      const int r = jb + c;                                  // pivot row / column: lane c, round 0
+      const double d = __shfl_sync(kFull, acc[0][c], c);
       ok = ok && (d > 0.0);
       const double inv = FAST ? fast_rsqrt3(d) : rsqrt(d);
       double lcol[RND];
 #pragma unroll
       for (int h = 0; h < RND; ++h) {
-        const int i = lane + 32 * h;
+        const int i = jb + lane + 32 * h;
         lcol[h] = acc[h][c] * inv;
         if (i >= r && i < R) Lw[lidxr<R>(i, r)] = lcol[h];
       }
       if (invd != nullptr && lane == 0) invd[r] = inv;
 #pragma unroll
       for (int c2 = c + 1; c2 < BW; ++c2) {
-        const int r2 = jb + c2;
-        double lsel = lcol[0];
-#pragma unroll
-        for (int h = 1; h < RND; ++h) if ((r2 >> 5) == h) lsel = lcol[h];
-        const double l2 = __shfl_sync(kFull, lsel, r2 & 31);   // L[r2][r]
+        const double l2 = __shfl_sync(kFull, lcol[0], c2);   // L[jb + c2][r]
 #pragma unroll
         for (int h = 0; h < RND; ++h) acc[h][c2] = fma(-lcol[h], l2, acc[h][c2]);
       }
@@ -170,8 +164,15 @@ __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double
     __syncwarp();
   };
   constexpr int NBLK = K / 4, TAIL = K % 4;
-  for (int b = 0; b < NBLK; ++b) block(4 * b, std::integral_constant<int, 4>{});
-  if constexpr (TAIL > 0) block(4 * NBLK, std::integral_constant<int, (TAIL > 0 ? TAIL : 1)>{});
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+  using I4 = std::integral_constant<int, 4>;
+  static_assert(R <= 64, "two rounds of rows");
+  for (int b = 0; b < NBLK; ++b) {
+    if (4 * b + 32 < R) block(4 * b, I4{}, I2{});
+    else block(4 * b, I4{}, I1{});
+  }
+  if constexpr (TAIL > 0) block(4 * NBLK, std::integral_constant<int, (TAIL > 0 ? TAIL : 1)>{}, I1{});
   return ok;
 }
 
