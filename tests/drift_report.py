@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import oracle_lib as orc
-    from parity import cov_err, state_err
+    from parity import all_errs
     pkg = importlib.import_module("slam-uwv_kalman_filters_b200")
     syn = importlib.import_module("slam-uwv_kalman_filters_b200.synthetic")
     DT = 0.01
@@ -68,10 +68,12 @@ def main():
                 gate_o += int(st & 4 != 0)
         if s in checkpoints:
             gmu, gcov = ukf.get_state()
-            es = max(state_err(gmu[f], omu[f]) for f in range(B))
-            ec = max(cov_err(gcov[f], ocov[f]) for f in range(B))
-            rows.append({"step": s, "state_rel_err": es, "cov_rel_err": ec})
-            print(f"step {s:6d}: state {es:.3e}  cov {ec:.3e}   ({time.time() - t0:.0f} s)", flush=True)
+            e = np.max([all_errs(gmu[f], gcov[f], omu[f], ocov[f]) for f in range(B)], axis=0)
+            es, ec = float(e[0]), float(e[1])
+            rows.append({"step": s, "state_rel_err": es, "cov_rel_err": ec, "state_per_component_err": float(e[2]),
+                         "cov_scaled_err": float(e[3])})
+            print(f"step {s:6d}: state {es:.3e}  cov {ec:.3e}  state(comp) {e[2]:.3e}  cov(scaled) {e[3]:.3e}   ({time.time() - t0:.0f} s)",
+                  flush=True)
     st = ukf.get_status()
     gate_g = int((st & 4 != 0).sum())
     res = {"steps": a.steps, "filters": B, "dt": DT, "sequence": "predict+DVL(dropout 2000..3500)+acc @100Hz, pressure @10Hz, ADCP gated @1Hz",
