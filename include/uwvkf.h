@@ -162,6 +162,17 @@ int uwvkf_pose_update(uwvkf_handle h, int meas_kind, const double *z, const doub
 int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int meas_kind, const double *z,
                               const double *R, int R_per_filter, const double *aux, const uint8_t *valid,
                               int memspace);
+/* The 100 Hz step of a full PoseUKF in ONE call: predictionStep(dt) (dt == 0: none) followed by integrateMeasurement(kind_a)
+ * and integrateMeasurement(kind_b) (src/PoseUKF.cpp:446-466, 476-490) -- e.g. DVL + accelerometer, BASELINE config 3.  It
+ * launches the fused predict + kind_a kernel and then the kind_b kernel.  (A single two-update kernel -- the panel of the
+ * covariance on chip between the three operations, the rest read and written once with both downdates -- exists for (VELOCITY,
+ * ACCELERATION) behind the build switch UWVKF_FUSED2: bit-identical, but slower than the two launches on B200, see
+ * DESIGN.md section 6b.)  w[B][3] (may be NULL: keep the stored rotation rate),
+ * z_a / z_b [B][m], R_a / R_b [m*m] shared by the batch, valid_a / valid_b [B] optional dropout masks.  Bit-identical to
+ * uwvkf_pose_set_rotation_rate + uwvkf_predict + uwvkf_pose_update(kind_a) + uwvkf_pose_update(kind_b). */
+int uwvkf_pose_predict_update2(uwvkf_handle h, double dt, const double *w, int kind_a, const double *z_a, const double *R_a,
+                               const uint8_t *valid_a, int kind_b, const double *z_b, const double *R_b, const uint8_t *valid_b,
+                               int memspace);
 /* integrateMeasurement(marker_features, feature_positions, marker_pose, cov_marker_pose, camera_config, camera_in_IMU)
  * (src/PoseUKF.cpp:613-654): the state is augmented with the marker pose (59 DOF, 119 sigma points), one S2 update per
  * feature, the leading 53 x 53 block is kept.  px[B][nfeat][2] pixel coordinates (memspace), pxcov[nfeat][4],

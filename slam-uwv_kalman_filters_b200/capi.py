@@ -66,6 +66,8 @@ def load_library():
         lib.uwvkf_pose_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_pose_predict_update.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_int]
+        lib.uwvkf_pose_predict_update2.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.uwvkf_pose_update_features.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int]
         lib.uwvkf_pose_get_navigation.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         lib.uwvkf_pose_reset_with_external_pose.argtypes = [C.c_void_p, C.c_void_p]
@@ -427,6 +429,13 @@ class PoseUKFBatch(_FilterBatch):
             valid = np.ascontiguousarray(valid, dtype=np.uint8)
         self._ck(self._lib.uwvkf_pose_predict_update(self._h, float(dt), _ptr(w), kind, _ptr(z), _ptr(R), per, _ptr(aux),
                                                      _ptr(valid), memspace))
+
+    def predict_update2(self, dt, w, kind_a, z_a, R_a, kind_b, z_b, R_b, valid_a=None, valid_b=None, memspace=HOST):
+        """predictionStep(dt) + integrateMeasurement(kind_a) + integrateMeasurement(kind_b) in one kernel (DVL + accelerometer:
+        the 100 Hz step of a full PoseUKF); dt = 0 skips the prediction."""
+        w, z_a, R_a, z_b, R_b = _f64(w), _f64(z_a), _f64(R_a), _f64(z_b), _f64(R_b)
+        self._ck(self._lib.uwvkf_pose_predict_update2(self._h, float(dt), _ptr(w), int(kind_a), _ptr(z_a), _ptr(R_a), _ptr(_u8(valid_a)),
+                                                      int(kind_b), _ptr(z_b), _ptr(R_b), _ptr(_u8(valid_b)), memspace))
 
     def step_host(self, dt, w_host, kind, z_host, R, aux=None, nav_out=None):
         """Pipelined host-buffer step (uwvkf_pose_step_host): rotation rate + predictionStep(dt) + integrateMeasurement(kind)

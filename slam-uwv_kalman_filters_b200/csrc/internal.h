@@ -36,8 +36,8 @@ struct uwvkf_filter_s {
   double mean_tol = 1e-9;
   int mean_max_it = 100;
   // staging for host inputs
-  double *d_z = nullptr, *d_Rpf = nullptr;
-  uint8_t *d_valid = nullptr;
+  double *d_z = nullptr, *d_Rpf = nullptr, *d_z2 = nullptr;
+  uint8_t *d_valid = nullptr, *d_valid2 = nullptr;
   double *d_tmp = nullptr;
   size_t tmp_bytes = 0;
   // PoseUKF

@@ -122,14 +122,24 @@ template <> struct FMeas<M_WATER_VELOCITY> {   // src/PoseUKF.cpp:133-151: prefi
   }
 };
 
-template <int HAS_PREDICT, int KIND>
+// KIND2 != M_NONE: a SECOND update in the same pass over the filter (predict + DVL + accelerometer, the 100 Hz step of BASELINE
+// config 3): the panel stays in shared memory between the updates, the trailing triangle is rewritten once, with both downdates.
+template <int HAS_PREDICT, int KIND, int KIND2 = M_NONE>
 struct FusedCfg {
   using MF = FMeas<KIND == M_NONE ? M_XY : KIND>;
-  static constexpr int KM = (KIND == M_NONE) ? 0 : MF::K;
-  static constexpr int NT = (KIND == M_NONE) ? 0 : MF::NT;
+  using MF2 = FMeas<KIND2 == M_NONE ? M_XY : KIND2>;
+  static_assert(KIND2 == M_NONE || KIND != M_NONE, "a second update needs a first");
+  static constexpr int KM1 = (KIND == M_NONE) ? 0 : MF::K;
+  static constexpr int KM2 = (KIND2 == M_NONE) ? 0 : MF2::K;
+  static constexpr int KM = KM1 > KM2 ? KM1 : KM2;
+  static constexpr int NT1 = (KIND == M_NONE) ? 0 : MF::NT;
+  static constexpr int NT2 = (KIND2 == M_NONE) ? 0 : MF2::NT;
+  static constexpr int NT = NT1 > NT2 ? NT1 : NT2;
   static constexpr int KA = (KIND == M_NONE) ? 0 : 6;                       // apply_delta prefix
   static constexpr int K0 = HAS_PREDICT ? 15 : 0;
-  static constexpr int KPM = (KIND == M_NONE) ? 0 : MF::KPMIN;
+  static constexpr int KPM1 = (KIND == M_NONE) ? 0 : MF::KPMIN;
+  static constexpr int KPM2 = (KIND2 == M_NONE) ? 0 : MF2::KPMIN;
+  static constexpr int KPM = KPM1 > KPM2 ? KPM1 : KPM2;
   static constexpr int KP0 = (K0 > KM ? (K0 > KA ? K0 : KA) : (KM > KA ? KM : KA));
   static constexpr int KP = KP0 > KPM ? KP0 : KPM;                          // panel width
   static constexpr int PANEL = KP * N - (KP * (KP - 1)) / 2;                // doubles in the panel
@@ -150,12 +160,15 @@ struct FusedCfg {
   static constexpr int O_L = PBUF + (TWO ? PBUF : 0);
   static constexpr int O_G = O_L + LSZ;          // per sigma-point pair j: {A[0][j], A[1][j], A[2][j], -}, AoS [KE][4]
   static constexpr int O_KC = O_G + 4 * KE;        // per column b: {K[b][0], K[b][1], K[b][2], f_b}, AoS [54][4] (two broadcast
-                                                   // 128-bit loads hand a whole warp everything column b contributes)
-  static constexpr int O_LT = O_KC + 4 * 54;           // rows T of the panel factor, NT x KE
-  // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M); two sets, alternating per filter (the next
-  // filter's inputs arrive while the current filter's update still reads its own)
+                                                   // 128-bit loads hand a whole warp everything column b contributes); with a
+                                                   // second update [54][8]: + {K2[b][0], K2[b][1], K2[b][2], -}
+  static constexpr int KCW = (KIND2 == M_NONE) ? 4 : 8;
+  static constexpr int O_LT = O_KC + KCW * 54;         // rows T of the panel factor, NT x KE
+  // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M), z of the second update [8..8+M2); two sets,
+  // alternating per filter (the next filter's inputs arrive while the current filter's update still reads its own)
+  static constexpr int INW = (KIND2 == M_NONE) ? 8 : 12;
   static constexpr int O_IN = O_LT + NT * KE;
-  static constexpr int TOTAL = O_IN + 16;
+  static constexpr int TOTAL = O_IN + 2 * INW;
   // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
@@ -476,6 +489,8 @@ __device__ __forceinline__ void process_panel_out(const double *SA, double *S, c
   }
 }
 
+__device__ const double kNoKs[2][3] = {{0, 0, 0}, {0, 0, 0}};
+
 // Trailing triangle (columns >= KP of the packed covariance, a contiguous suffix of the filter block), streamed HBM -> registers
 // -> HBM once:   s <- f_a f_b s + dt^2 Q_ab - sum_c (K S)_ac K_bc.
 // Rows keep the owner they have everywhere else in the kernel (x0 = lane, x1 = lane + 32), so the row factors f_a, (K S)_a live in
@@ -485,16 +500,18 @@ __device__ __forceinline__ void process_panel_out(const double *SA, double *S, c
 // x0 on lanes 21..31 (rows 21..31); columns b <= 20 need a second, short access for the rows b..20 ("secondary" row x0 of lanes
 // <= 20).  No entry -> (row, column) table, no gathers, no dependent address arithmetic: every column is independent of every
 // other, so the loads of a whole batch of columns are in flight before the first is consumed.
-template <bool AP, bool AK, int KP, int M, int UB, int DEPTH>
+// M2 > 0: a second rank-M2 downdate (two-update kernels; KC rows are then 8 wide, K2 in slots 4..6, ks2 its row factors).
+template <bool AP, bool AK, int KP, int M, int UB, int DEPTH, int M2 = 0>
 __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const double *Qs, const double *KC, const double (&f)[2],
-                                              const double (&ks)[2][3], double q2add, int lane) {
+                                              const double (&ks)[2][3], double q2add, int lane, const double (&ks2)[2][3] = kNoKs) {
+  constexpr int KCW = M2 > 0 ? 8 : 4;
   const bool lo = lane <= 20;
   const int rP = lo ? lane + 32 : lane;
   const double fP = lo ? f[1] : f[0];
   const double kP0 = lo ? ks[1][0] : ks[0][0], kP1 = lo ? ks[1][1] : ks[0][1], kP2 = lo ? ks[1][2] : ks[0][2];
   auto entry = [&](int b, int row, double sv, double fr, double k0, double k1, double k2) {
-    const double2 c01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
-    const double2 c2f = *reinterpret_cast<const double2 *>(KC + 4 * b + 2);
+    const double2 c01 = *reinterpret_cast<const double2 *>(KC + KCW * b);
+    const double2 c2f = *reinterpret_cast<const double2 *>(KC + KCW * b + 2);
     if (AP) {
       sv = fma(fr * c2f.y, sv, Qs[coloff(b) + row]);
       if (b >= T_WV && b < T_BADCP && row == b) sv += q2add;
@@ -503,6 +520,13 @@ __device__ __forceinline__ void trailing_pass(double *__restrict__ gS, const dou
       sv = fma(-k0, c01.x, sv);
       if (M > 1) sv = fma(-k1, c01.y, sv);
       if (M > 2) sv = fma(-k2, c2f.x, sv);
+    }
+    if constexpr (M2 > 0) {   // second downdate; the row factors are re-selected here (cold path: refused filters only)
+      const bool pr = (row >= 32);
+      const double2 d01 = *reinterpret_cast<const double2 *>(KC + KCW * b + 4);
+      sv = fma(-(pr ? ks2[1][0] : ks2[0][0]), d01.x, sv);
+      if (M2 > 1) sv = fma(-(pr ? ks2[1][1] : ks2[0][1]), d01.y, sv);
+      if (M2 > 2) sv = fma(-(pr ? ks2[1][2] : ks2[0][2]), KC[KCW * b + 6], sv);
     }
     return sv;
   };
@@ -570,8 +594,9 @@ __device__ __noinline__ void trailing_pass_cold(double *gS, const double *Qs, co
 // L2 latency (the triangle was prefetched at the top of the filter) hides behind that phase, and the FMAs / stores of the
 // previous batch fill the issue slots the phase leaves empty.  Nothing is stored before the factorisation of apply_delta has
 // succeeded (a failure rolls the update back: the batches in flight are dropped and the classic pass applies the process map only).
-template <bool AP, int KP, int M, int UB, int DEPTH>
+template <bool AP, int KP, int M, int UB, int DEPTH, int M2 = 0>
 struct TrailStream {
+  static constexpr int KCW = M2 > 0 ? 8 : 4;
   static constexpr int NB = (N - KP + UB - 1) / UB;
   static constexpr int NS = KP <= 20 ? 21 - KP : 0;
   double v[DEPTH][UB];
@@ -580,9 +605,9 @@ struct TrailStream {
   // offsets recomputed from an opaque copy of the lane index (a value the compiler could prove loop invariant would be hoisted
   // out of the filter loop -- some 90 lane-dependent offsets -- and spilled to local memory, which this kernel serves at L2 latency)
   __device__ __forceinline__ static double entry(const double *Qs, const double *KC, double q2add, int b, int row, double sv, double fr,
-                                                 double k0, double k1, double k2) {
-    const double2 c01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
-    const double2 c2f = *reinterpret_cast<const double2 *>(KC + 4 * b + 2);
+                                                 double k0, double k1, double k2, double j0 = 0.0, double j1 = 0.0, double j2 = 0.0) {
+    const double2 c01 = *reinterpret_cast<const double2 *>(KC + KCW * b);
+    const double2 c2f = *reinterpret_cast<const double2 *>(KC + KCW * b + 2);
     if (AP) {
       sv = fma(fr * c2f.y, sv, Qs[coloff(b) + row]);
       if (b >= T_WV && b < T_BADCP && row == b) sv += q2add;
@@ -590,6 +615,12 @@ struct TrailStream {
     sv = fma(-k0, c01.x, sv);
     if (M > 1) sv = fma(-k1, c01.y, sv);
     if (M > 2) sv = fma(-k2, c2f.x, sv);
+    if constexpr (M2 > 0) {   // downdate of the second update: K2 in slots 4..6 of the column table, (K2 S2) rows j0..j2
+      const double2 d01 = *reinterpret_cast<const double2 *>(KC + KCW * b + 4);
+      sv = fma(-j0, d01.x, sv);
+      if (M2 > 1) sv = fma(-j1, d01.y, sv);
+      if (M2 > 2) sv = fma(-j2, KC[KCW * b + 6], sv);
+    }
     return sv;
   }
   template <int I> __device__ __forceinline__ void load(const double *gS, int lane) {
@@ -612,12 +643,14 @@ struct TrailStream {
     for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lane <= 20 && lane >= KP + u) ? lane : KP + u));
   }
   template <int I> __device__ __forceinline__ void finish(bool on, double *gS, const double *Qs, const double *KC, const double (&f)[2],
-                                                          const double (&ks)[2][3], double q2add, int lane) {
+                                                          const double (&ks)[2][3], double q2add, int lane,
+                                                          const double (&ks2)[2][3] = kNoKs) {
     if constexpr (I < NB) {
       const bool lo = lane <= 20;
       const int rP = lo ? lane + 32 : lane;
       const double fP = lo ? f[1] : f[0];
       const double kP0 = lo ? ks[1][0] : ks[0][0], kP1 = lo ? ks[1][1] : ks[0][1], kP2 = lo ? ks[1][2] : ks[0][2];
+      const double jP0 = lo ? ks2[1][0] : ks2[0][0], jP1 = lo ? ks2[1][1] : ks2[0][1], jP2 = lo ? ks2[1][2] : ks2[0][2];
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const int b = KP + I * UB + u;
@@ -632,20 +665,22 @@ struct TrailStream {
 #elif UWVKF_EXP_NOSTORE  // experiment: no stores (WRONG results; timing only)
           if (entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2) == 1.2345e-300) stcs_if(on && rP >= b, gS + coloff(b) + rowP, 0.0);
 #else
-          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2));
+          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2, jP0, jP1, jP2));
 #endif
         }
       }
     }
   }
   __device__ __forceinline__ void finish_secondary(bool on, double *gS, const double *Qs, const double *KC, const double (&f)[2],
-                                                   const double (&ks)[2][3], double q2add, int lane) {
+                                                   const double (&ks)[2][3], double q2add, int lane,
+                                                   const double (&ks2)[2][3] = kNoKs) {
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
       const int b = KP + u;
       const bool actS = lane <= 20 && lane >= b;
       const int rowS = actS ? lane : b;
-      stcs_if(on && actS, gS + coloff(b) + rowS, entry(Qs, KC, q2add, b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2]));
+      stcs_if(on && actS, gS + coloff(b) + rowS,
+              entry(Qs, KC, q2add, b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2], ks2[0][0], ks2[0][1], ks2[0][2]));
     }
   }
 };
@@ -665,9 +700,10 @@ __device__ inline double markov_rate(int s, const Params &P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int HAS_PREDICT, int KIND, int WARPS>
+template <int HAS_PREDICT, int KIND, int WARPS, int KIND2 = M_NONE>
 __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
-  using C = FusedCfg<HAS_PREDICT, KIND>;
+  using C = FusedCfg<HAS_PREDICT, KIND, KIND2>;
+  constexpr int KCW = C::KCW;
   constexpr int KP = C::KP, KE = C::KE;
   extern __shared__ __align__(16) double smem[];
   double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
@@ -695,12 +731,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     __syncthreads();
     // per-warp column table {K_b (zero until an update fills it), f_b}
     for (int b = lane; b < 54; b += 32) {
-      KC[4 * b] = 0.0; KC[4 * b + 1] = 0.0; KC[4 * b + 2] = 0.0; KC[4 * b + 3] = ftab[b];
+#pragma unroll
+      for (int k = 0; k < KCW; ++k) KC[KCW * b + k] = (k == 3) ? ftab[b] : 0.0;
     }
     __syncwarp();
   }
   const Op &op0 = a.ops[0];
   const Op &opu = a.ops[HAS_PREDICT ? 1 : 0];
+  const Op &opu2 = a.ops[HAS_PREDICT ? 2 : 1];   // second update (two-update kernels only)
+  (void)opu2;
   const double dt = HAS_PREDICT ? op0.dt : 0.0;
   const double dt2 = dt * dt;
   const int x0 = lane, x1 = lane + 32;
@@ -721,11 +760,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     for (int k = lane; k < NV; k += 32)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta + 16u * k), "l"(src + 16 * k) : "memory");
     // the filter's small inputs ride in the same group, so no global-memory round trip is left inside the iteration
-    const unsigned ina = w_saddr + 8u * (C::O_IN + 8u * pr);
+    const unsigned ina = w_saddr + 8u * (C::O_IN + (unsigned)C::INW * pr);
     if (HAS_PREDICT && lane < 3)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(a.rot_rate + ff * 3 + lane) : "memory");
     if (KIND != M_NONE && lane >= 4 && lane < 4 + C::MF::M)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(opu.z + ff * C::MF::M + (lane - 4)) : "memory");
+    if (KIND2 != M_NONE && lane >= 8 && lane < 8 + C::MF2::M)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(opu2.z + ff * C::MF2::M + (lane - 8)) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   {
@@ -735,7 +776,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 
   for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
     double *blk = a.state + f * BLK;
-    const double *const inb = w + C::O_IN + 8 * par;   // this filter's inputs
+    const double *const inb = w + C::O_IN + C::INW * par;   // this filter's inputs
 #if UWVKF_OPAQUE_LANE
     // The lane index is made opaque once per filter: everything derived from it inside the loop (row predicates, packed column
     // offsets, sigma-point signs -- well over a hundred values) would otherwise be proven loop invariant, hoisted out of the
@@ -775,10 +816,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     }
     __syncwarp();
     unsigned st = 0;
-    bool predicted = false, updated = false, trailing_done = false;
-    (void)trailing_done;
+    bool predicted = false, updated = false, updated2 = false, trailing_done = false;
+    (void)trailing_done; (void)updated2;
     double add = 0.0;
     double ksr[2][3] = {{0, 0, 0}, {0, 0, 0}};   // (K S) rows of the accepted update for the rows this lane owns
+    double ksr2[2][3] = {{0, 0, 0}, {0, 0, 0}};  // the same for the second update (two-update kernels)
+    (void)ksr2;
 
     // =================================== predict (k = 15) ====================================================
     if constexpr (HAS_PREDICT) {
@@ -898,14 +941,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     }
 
     // =================================== update (k = Meas::K) + apply_delta (k = 6) ==========================
-    if constexpr (KIND != M_NONE) {
-      using MM = FMeas<KIND>;
+    // One update as a generic lambda: a two-update kernel runs it twice on the panel in shared memory.  SECOND = the second
+    // update of such a kernel; DEFER = its first, whose share of the trailing triangle is left to the pass of the second.
+    auto do_update = [&](auto kind_, auto second_, const Op &opu, const double *zin) {
+      constexpr int KINDX = decltype(kind_)::value;
+      constexpr bool SECOND = decltype(second_)::value;
+      constexpr bool DEFER = (KIND2 != M_NONE) && !SECOND;
+      constexpr int KOFF = SECOND ? 4 : 0;      // slots of this update's gain in the column table
+      double (&ksx)[2][3] = *(SECOND ? &ksr2 : &ksr);
+      bool accepted = false;
+      using MM = FMeas<KINDX>;
       constexpr int K = MM::K, M = MM::M, NT = MM::NT;
       constexpr int NPTS = 2 * K + 1, ROUNDS = (NPTS + 31) / 32;
       static_assert(NT == 0 || (MM::tail(0) >= K && K <= 32), "tail coordinates lie behind the prefix");
+      static_assert(!SECOND || NT == 0 || MM::tail(NT - 1) < KP, "the second update must find its tail coordinates in the panel");
       // entry (ta, tb), ta >= tb >= KP, of the covariance the update works on: the trailing triangle still holds the
       // pre-predict values in HBM, so the process map is applied on the fly (same expression as the write-back pass)
       auto trailing = [&](int ta, int tb) {
+        // (a second update never gets here: its tail coordinates must lie inside the panel, checked below)
         const int e = coloff(tb) + ta;
         double sv = (blk + OFF_S)[e];
         if (HAS_PREDICT && predicted) {
@@ -923,13 +976,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       if (go) {
         bool bad = false;
 #pragma unroll
-        for (int k = 0; k < M; ++k) { z[k] = inb[4 + k]; bad |= isnan(z[k]); }
+        for (int k = 0; k < M; ++k) { z[k] = zin[k]; bad |= isnan(z[k]); }
 #pragma unroll
         for (int k = 0; k < M * M; ++k) { Rm[k] = opu.Rdev ? opu.Rdev[f * M * M + k] : opu.R[k]; bad |= isnan(Rm[k]); }
         if (bad) { st |= ST_NAN_MEAS; go = false; }
       }
       if (go) {
-        if constexpr (KIND == M_XY) {
+        if constexpr (KINDX == M_XY) {
           if (opu.kind == M_GEOGRAPHIC) {   // reference src/PoseUKF.cpp:572-578
             double px, py;
             tmerc_world_to_nav(P.tm, z[0], z[1], px, py);
@@ -1100,14 +1153,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
           for (int b = 0; b < M; ++b) d2 += nu[i] * Si[i * M + b] * nu[b];
         // d2p95: GeographicPosition (reference src/PoseUKF.cpp:578) and the ADCP update (:610)
-        const bool gate95 = ((KIND == M_XY) && opu.kind == M_GEOGRAPHIC) || KIND == M_WATER_VELOCITY;
+        const bool gate95 = ((KINDX == M_XY) && opu.kind == M_GEOGRAPHIC) || KINDX == M_WATER_VELOCITY;
         if (gate95 && d2 > 5.991) {
           st |= ST_GATE_REJECTED;
         } else {
           // gain rows, (K S) rows and delta for the rows this lane owns; K and K S go straight to the row tables the
           // trailing pass reads (and are re-read from there in the rare rollback) so that they do not stay in registers
           double dl[2], kk[2][3] = {{0, 0, 0}, {0, 0, 0}};
-          double (&ks)[2][3] = ksr;
+          double (&ks)[2][3] = ksx;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             double dx = 0;
@@ -1133,16 +1186,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           for (int h = 0; h < 2; ++h) {
             const int x = lane + 32 * h;
             if (x < N) {
-              *reinterpret_cast<double2 *>(KC + 4 * x) = make_double2(kk[h][0], kk[h][1]);
-              KC[4 * x + 2] = kk[h][2];
+              *reinterpret_cast<double2 *>(KC + KCW * x + KOFF) = make_double2(kk[h][0], kk[h][1]);
+              KC[KCW * x + KOFF + 2] = kk[h][2];
             }
           }
           __syncwarp();
           PH(18);
           // interleaved trailing pass (TrailStream): the first batches are requested now and fly during the panel downdate and
           // the factorisation of apply_delta
-          constexpr bool ILV = UWVKF_ILV && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY);
-          TrailStream<HAS_PREDICT != 0, KP, M, UWVKF_ILV_UB, UWVKF_ILV_DEPTH> ts;
+          constexpr bool ILV = UWVKF_ILV && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY) && !DEFER;
+          constexpr int M1_ = SECOND ? C::MF::M : M, M2_ = SECOND ? M : 0;   // the pass of a second update carries both downdates
+          TrailStream<HAS_PREDICT != 0, KP, M1_, UWVKF_ILV_UB, UWVKF_ILV_DEPTH, M2_> ts;
           // Filters whose prediction was refused (rare) still run the batches -- no branch around loads whose values are consumed
           // several phases later -- but with every store predicated off; the classic pass then handles them
           const bool ilv = ILV && (HAS_PREDICT ? predicted : true);
@@ -1154,7 +1208,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #endif
           auto ts_step = [&](auto i_) {   // batch I out, batch I + DEPTH in
             constexpr int I = decltype(i_)::value;
-            ts.template finish<I>(ilv, tgS, Qs, KC, frow, ksr, tq2, tl);
+            ts.template finish<I>(ilv, tgS, Qs, KC, frow, ksr, tq2, tl, ksr2);
             ts.template load<I + UWVKF_ILV_DEPTH>(tgS, tl);
           };
 #if UWVKF_ILV_EARLY
@@ -1169,8 +1223,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll
           for (int b = 0; b < KP; ++b) {
             const int cb = coloff(b);
-            const double2 k01 = *reinterpret_cast<const double2 *>(KC + 4 * b);
-            const double k0 = k01.x, k1 = k01.y, k2 = KC[4 * b + 2];
+            const double2 k01 = *reinterpret_cast<const double2 *>(KC + KCW * b + KOFF);
+            const double k0 = k01.x, k1 = k01.y, k2 = KC[KCW * b + KOFF + 2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int x = lane + 32 * h;
@@ -1210,7 +1264,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             const int j = (p - 1) >> 1;
             const double sg = (p & 1) ? 1.0 : -1.0;
             auto d = [&](int t) { return (on && t >= j) ? sg * Lw[j * LStride<KA> + t] : 0.0; };
-            if constexpr (ILV) { ts.finish_secondary(ilv, tgS, Qs, KC, frow, ksr, tq2, tl); ts_step(std::integral_constant<int, 0>{}); }
+            if constexpr (ILV) { ts.finish_secondary(ilv, tgS, Qs, KC, frow, ksr, tq2, tl, ksr2); ts_step(std::integral_constant<int, 0>{}); }
             Quat qp = so3_boxplus(q, Vec3{d3 + d(3), d4 + d(4), d5 + d(5)}, 1.0);
             PH(21);
             if constexpr (ILV) ts_step(std::integral_constant<int, 1>{});
@@ -1243,6 +1297,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             if (x1 < N) mu[x1 + 1] += dl[1];
             if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
             updated = true;
+            accepted = true;
+            if constexpr (SECOND) updated2 = true;
             if constexpr (ILV) {
               ts_step(std::integral_constant<int, 4>{}); ts_step(std::integral_constant<int, 5>{});
               ts_step(std::integral_constant<int, 6>{}); ts_step(std::integral_constant<int, 7>{});
@@ -1257,24 +1313,48 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #pragma unroll 1
             for (int b = 0; b < KP; ++b) {
               const int cb = coloff(b);
-              const double k0 = KC[4 * b], k1 = KC[4 * b + 1], k2 = KC[4 * b + 2];
+              const double k0 = KC[KCW * b + KOFF], k1 = KC[KCW * b + KOFF + 1], k2 = KC[KCW * b + KOFF + 2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int x = lane + 32 * h;
                 if (x >= b && x < N) {
                   double s = S[cb + x];
-                  s = fma(ksr[h][0], k0, s);
-                  if (M > 1) s = fma(ksr[h][1], k1, s);
-                  if (M > 2) s = fma(ksr[h][2], k2, s);
+                  s = fma(ksx[h][0], k0, s);
+                  if (M > 1) s = fma(ksx[h][1], k1, s);
+                  if (M > 2) s = fma(ksx[h][2], k2, s);
                   S[cb + x] = s;
                 }
               }
             }
             __syncwarp();
+            if constexpr (KIND2 != M_NONE) {   // a dropped update contributes nothing to the (shared) trailing pass
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ksx[h][c] = 0.0;
+            }
           }
         }
       }
-    }
+      if constexpr (KIND2 != M_NONE) {
+        // The trailing pass of a two-update kernel always applies both downdates; an update that was refused (dropout mask, NaN,
+        // gate, lost definiteness) has zero (K S) rows, and its slots of the column table are cleared as well, so that a
+        // non-finite gain left there by an earlier, degenerate filter of this warp cannot leak in as 0 x NaN
+        if (!accepted) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int x = lane + 32 * h;
+            if (x < 54) {
+              *reinterpret_cast<double2 *>(KC + KCW * x + KOFF) = make_double2(0.0, 0.0);
+              KC[KCW * x + KOFF + 2] = 0.0;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    };
+    if constexpr (KIND != M_NONE) do_update(std::integral_constant<int, KIND>{}, std::false_type{}, opu, inb + 4);
+    if constexpr (KIND2 != M_NONE) do_update(std::integral_constant<int, KIND2>{}, std::true_type{}, opu2, inb + 8);
 
     // =================================== write back ===========================================================
     PH(27);
@@ -1311,6 +1391,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #endif
       if (trailing_done || UWVKF_EXP_SKIPTRAIL) {
         // the interleaved pass (TrailStream) has already rewritten the trailing triangle
+      } else if constexpr (KIND2 != M_NONE) {   // both downdates in one pass; refused updates carry zero factors
+        if (HAS_PREDICT && predicted) trailing_pass<true, true, KP, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
+        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
       } else if constexpr (KIND == M_NONE) {
         trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       } else if constexpr (!HAS_PREDICT) {

@@ -273,6 +273,17 @@ namespace {
 #ifndef UWVKF_UPDATE_WARPS
 #define UWVKF_UPDATE_WARPS UWVKF_FUSED_MAX_WARPS
 #endif
+// 1: uwvkf_pose_predict_update2 runs (DVL, accelerometer) as ONE two-update kernel.  Measured on 262,144 filters: predict + DVL +
+// accelerometer 5.00 ms against 2.49 + 1.43 ms for the fused predict + DVL kernel followed by the accelerometer kernel (the
+// two-update kernel issues at 35 % instead of 47 %: 7,660 instructions per filter-step, spilled loop invariants, twice the
+// instruction-cache misses); DVL + accelerometer without a predict 2.56 against 2.71 ms.  Off: the entry point launches twice.
+#ifndef UWVKF_FUSED2
+#define UWVKF_FUSED2 0
+#endif
+#ifndef UWVKF_FUSED2_WARPS
+#define UWVKF_FUSED2_WARPS 12
+#endif
+constexpr int kFused2Warps = UWVKF_FUSED2_WARPS;
 constexpr int kFastWarps = 12, kSlowWarps = 6, kEffortsVelWarps = 10, kFusedMaxWarps = UWVKF_FUSED_MAX_WARPS, kUpdateMaxWarps = UWVKF_UPDATE_WARPS;
 constexpr int kChunk = 4096;  // filters per staging chunk in set/get_state
 
@@ -353,26 +364,27 @@ int launch_pose(uwvkf_handle h, const pose::Launch &L) {
 }
 
 // v2 fused kernel (pose_fused.cuh): WARPS per CTA is chosen per instantiation from its shared-memory footprint
-template <int HP, int KIND>
+template <int HP, int KIND, int KIND2 = pose::M_NONE>
 constexpr int fused_warps() {
-  using C = pose::FusedCfg<HP, KIND>;
+  using C = pose::FusedCfg<HP, KIND, KIND2>;
   int w = (232448 - C::CTA * 8) / (C::TOTAL * 8);
-  const int cap = HP ? kFusedMaxWarps : kUpdateMaxWarps;   // update-only kernels carry far less register state
+  // update-only kernels carry far less register state; two-update kernels more (UWVKF_FUSED2_WARPS)
+  const int cap = KIND2 != pose::M_NONE ? kFused2Warps : (HP ? kFusedMaxWarps : kUpdateMaxWarps);
   return w > cap ? cap : w;
 }
-template <int HP, int KIND>
+template <int HP, int KIND, int KIND2 = pose::M_NONE>
 int launch_fused(uwvkf_handle h, const pose::Launch &L) {
-  using C = pose::FusedCfg<HP, KIND>;
-  constexpr int WARPS = fused_warps<HP, KIND>();
+  using C = pose::FusedCfg<HP, KIND, KIND2>;
+  constexpr int WARPS = fused_warps<HP, KIND, KIND2>();
   size_t smem = (size_t)(C::CTA + WARPS * C::TOTAL) * sizeof(double);
   static unsigned long long attr_set = 0;   // one bit per device
   if (!(attr_set >> h->device & 1ull)) {
-    CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pose::pose_fused_kernel<HP, KIND, WARPS, KIND2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set |= 1ull << h->device;
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
-  pose::pose_fused_kernel<HP, KIND, WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
+  pose::pose_fused_kernel<HP, KIND, WARPS, KIND2><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
   CK(cudaGetLastError());
   h->launches++;
   return UWVKF_OK;
@@ -414,6 +426,14 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
     if (nops == 1 && ops[0].type == 0) return launch_fused<1, pose::M_NONE>(h, L);
     if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
     if (nops == 2 && ops[0].type == 0 && ops[1].type == 1) return launch_fused_kind<1>(h, L, ops[1].kind);
+#if UWVKF_FUSED2
+    // the 100 Hz step of a full PoseUKF (BASELINE config 3): predict + DVL + accelerometer in ONE pass over the filter
+    if (nops == 3 && ops[0].type == 0 && ops[1].type == 1 && ops[2].type == 1 && ops[1].kind == UWVKF_POSE_VELOCITY &&
+        ops[2].kind == UWVKF_POSE_ACCELERATION)
+      return launch_fused<1, pose::M_VELOCITY, pose::M_ACCELERATION>(h, L);
+    if (nops == 2 && ops[0].type == 1 && ops[1].type == 1 && ops[0].kind == UWVKF_POSE_VELOCITY && ops[1].kind == UWVKF_POSE_ACCELERATION)
+      return launch_fused<0, pose::M_VELOCITY, pose::M_ACCELERATION>(h, L);
+#endif
   }
   // the velocity-only body-efforts update reads prefix 9 only: prefix-19 engine with six-row tables, 10 warps per SM
   if (!force_v1 && dense_only && !full_efforts && nops == 1) return launch_pose<20, kEffortsVelWarps>(h, L);
@@ -435,7 +455,7 @@ int stage(uwvkf_handle h, const void *src, size_t bytes, size_t cap, int memspac
 namespace {
 
 int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, int R_per_filter, const double *aux,
-                   const uint8_t *valid, int memspace, pose::Op &op) {
+                   const uint8_t *valid, int memspace, pose::Op &op, int slot = 0) {
   const int m = meas_dim(kind);
   if (m < 0) return fail(UWVKF_ERR_INVALID_ARGUMENT, "unknown PoseUKF measurement kind");
   if (!z || !R) return fail(UWVKF_ERR_INVALID_ARGUMENT, "z and R must not be NULL");
@@ -448,10 +468,13 @@ int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, i
     if (any_nan(R, R_per_filter ? h->B * m * m : m * m)) return fail(UWVKF_ERR_NAN_MEASUREMENT, "measurement covariance contains NaN");
   }
   const void *p;
-  int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * pose::MAXM * sizeof(double), memspace, (void **)&h->d_z, &p);
+  // (slot 1: the second update of a two-update call has its own staging buffers)
+  int rc = stage(h, z, (size_t)h->B * m * sizeof(double), (size_t)h->B * pose::MAXM * sizeof(double), memspace,
+                 (void **)(slot ? &h->d_z2 : &h->d_z), &p);
   if (rc) return rc;
   op.z = (const double *)p;
   if (R_per_filter) {
+    if (slot) return fail(UWVKF_ERR_UNSUPPORTED, "per-filter R is not available for the second update of a fused call");
     if (m > 3) return fail(UWVKF_ERR_UNSUPPORTED, "per-filter R is supported for measurement dimensions <= 3");
     rc = stage(h, R, (size_t)h->B * m * m * sizeof(double), (size_t)h->B * 9 * sizeof(double), memspace, (void **)&h->d_Rpf, &p);
     if (rc) return rc;
@@ -459,7 +482,7 @@ int make_update_op(uwvkf_handle h, int kind, const double *z, const double *R, i
   } else {
     for (int k = 0; k < m * m; ++k) op.R[k] = R[k];
   }
-  rc = stage(h, valid, (size_t)h->B, (size_t)h->B, memspace, (void **)&h->d_valid, &p);
+  rc = stage(h, valid, (size_t)h->B, (size_t)h->B, memspace, (void **)(slot ? &h->d_valid2 : &h->d_valid), &p);
   if (rc) return rc;
   op.valid = (const uint8_t *)p;
   if (aux) {
@@ -531,6 +554,7 @@ int uwvkf_destroy(uwvkf_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
   cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp); cudaFree(h->d_uwv);
+  cudaFree(h->d_z2); cudaFree(h->d_valid2);
   if (h->pipe) {
     auto *p = h->pipe;
     if (p->s_in) cudaStreamSynchronize(p->s_in);
@@ -793,6 +817,30 @@ int uwvkf_pose_predict_update(uwvkf_handle h, double dt, const double *w, int me
   int rc = make_update_op(h, meas_kind, z, R, R_per_filter, aux, valid, memspace, ops[1]);
   if (rc) return rc;
   return run_pose(h, 2, ops);
+}
+
+int uwvkf_pose_predict_update2(uwvkf_handle h, double dt, const double *w, int kind_a, const double *z_a, const double *R_a,
+                               const uint8_t *valid_a, int kind_b, const double *z_b, const double *R_b, const uint8_t *valid_b,
+                               int memspace) {
+  REQUIRE(h, UWVKF_FILTER_POSE);
+  if (std::isnan(dt) || dt < 0.0) return fail(UWVKF_ERR_INVALID_ARGUMENT, "dt must be >= 0");
+  if (w) {
+    int rc = uwvkf_pose_set_rotation_rate(h, w, memspace);
+    if (rc) return rc;
+  }
+  pose::Op ops[3];
+  std::memset(&ops[0], 0, sizeof ops[0]);
+  ops[0].type = 0; ops[0].dt = dt;
+  int rc = make_update_op(h, kind_a, z_a, R_a, 0, nullptr, valid_a, memspace, ops[1], 0);
+  if (rc) return rc;
+  rc = make_update_op(h, kind_b, z_b, R_b, 0, nullptr, valid_b, memspace, ops[2], 1);
+  if (rc) return rc;
+  const bool pair_fused = UWVKF_FUSED2 && kind_a == UWVKF_POSE_VELOCITY && kind_b == UWVKF_POSE_ACCELERATION;
+  if (pair_fused) return dt > 0.0 ? run_pose(h, 3, ops) : run_pose(h, 2, ops + 1);
+  // any other pair: the same result from two launches (fused predict + first update, then the second update)
+  rc = dt > 0.0 ? run_pose(h, 2, ops) : run_pose(h, 1, ops + 1);
+  if (rc) return rc;
+  return run_pose(h, 1, ops + 2);
 }
 
 int uwvkf_pose_update_features(uwvkf_handle h, int nfeat, const double *px, const double *pxcov, const double *feature_pos,

@@ -156,6 +156,65 @@ def test_fused_step_equals_separate_calls(pkg, syn, scen):
     a.close(); b.close()
 
 
+def test_two_update_step_equals_separate_calls(pkg, syn, scen):
+    """predictionStep + DVL + accelerometer in ONE kernel (uwvkf_pose_predict_update2) is bit-identical to the three separate
+    calls -- also with dropout masks on either update, without a prediction (dt = 0), and for a pair that is not fused."""
+    B = 96
+    a, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    b, *_ = make_batch(pkg, syn, scen, B)
+    va = (np.arange(B) % 3 != 0).astype(np.uint8)          # DVL dropouts
+    vb = (np.arange(B) % 5 != 1).astype(np.uint8)          # accelerometer dropouts
+    for s in range(1, 6):
+        inp = syn.pose_inputs(filt, s)
+        ma_, mb_ = (va, vb) if s >= 3 else (None, None)
+        dt = 0.0 if s == 5 else DT
+        a.predict_update2(dt, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC,
+                          valid_a=ma_, valid_b=mb_)
+        b.integrate_rotation_rate(inp["gyro"])
+        if dt > 0:
+            b.prediction_step(dt)
+        b.integrate_measurement(pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, valid=ma_)
+        b.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC, valid=mb_)
+        ma, ca = a.get_state()
+        mb, cb = b.get_state()
+        assert np.array_equal(ma, mb) and np.array_equal(ca, cb), f"step {s}"
+    assert not a.get_status().any() and not b.get_status().any()
+    # parity of the fused step against the oracle (one more step from the common state)
+    inp = syn.pose_inputs(filt, 6)
+    mu0, cov0 = a.get_state()
+    a.predict_update2(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL, pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+    gmu, gcov = a.get_state()
+    omu, ocov = oracle_predict(mu0, cov0, scen, inp["gyro"], off)
+    omu, ocov, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, inp["dvl"], syn.R_DVL, None, inp["gyro"])
+    omu, ocov, _ = oracle_update(orc.ACCELERATION, omu, ocov, scen, inp["acc"], syn.R_ACC, None, inp["gyro"])
+    assert_parity(gmu, gcov, omu, ocov, "fused predict + DVL + accelerometer")
+    # a NaN sample in the second update: that filter keeps prediction + first update, the others are untouched by it
+    zb = inp["acc"].copy(); zb[7, 0] = np.nan
+    import torch
+    zbd, zad, wd = torch.from_numpy(zb).cuda(), torch.from_numpy(inp["dvl"]).cuda(), torch.from_numpy(inp["gyro"]).cuda()
+    b.set_state(mu0, cov0); a.set_state(mu0, cov0)
+    a.predict_update2(DT, wd.data_ptr(), pkg.POSE_VELOCITY, zad.data_ptr(), syn.R_DVL, pkg.POSE_ACCELERATION, zbd.data_ptr(), syn.R_ACC,
+                      memspace=pkg.DEVICE)
+    b.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    m7, c7 = b.get_state(first=7, count=1)
+    b.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma[7], m7[0]) and np.array_equal(ca[7], c7[0]) and a.get_status()[7] & pkg.ST_NAN_MEASUREMENT
+    keep = np.arange(B) != 7
+    assert np.array_equal(ma[keep], mb[keep]) and np.array_equal(ca[keep], cb[keep])
+    # an unfused pair (XY + Z) gives the sequential result through the same entry point
+    a.clear_status()
+    xy, zz = ma[:, 0:2] + 0.05, ma[:, 2:3] - 0.02
+    Rxy, Rz = 0.04 * np.eye(2), np.array([[0.0025]])
+    a.predict_update2(DT, inp["gyro"], pkg.POSE_XY, xy, Rxy, pkg.POSE_Z, zz, Rz)
+    b.set_state(ma, ca)
+    b.predict_update(DT, inp["gyro"], pkg.POSE_XY, xy, Rxy)
+    b.integrate_measurement(pkg.POSE_Z, zz, Rz)
+    assert all(np.array_equal(x, y) for x, y in zip(a.get_state(), b.get_state()))
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("kind", ["pressure", "adcp", "acceleration", "z"])
 def test_fused_predict_update_parity(pkg, syn, scen, kind):
     """predictionStep + integrateMeasurement(kind) in ONE kernel vs the oracle's two calls.  For pressure / ADCP this

@@ -93,6 +93,12 @@ def main():
     timeit_fast("pose update adcp", upd(pkg.POSE_WATER_VELOCITY, d["adcp"], syn.R_ADCP, np.array([0.5])), B, P, ukf)
     timeit_fast("pose fused predict+DVL", lambda: ukf.predict_update(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
                                                                   syn.R_DVL, memspace=pkg.DEVICE), B, P, ukf)
+    timeit_fast("pose fused predict+DVL+accelerometer", lambda: ukf.predict_update2(DT, d["gyro"].data_ptr(), pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
+                                                                               syn.R_DVL, pkg.POSE_ACCELERATION, d["acc"].data_ptr(), syn.R_ACC,
+                                                                               memspace=pkg.DEVICE), B, P, ukf)
+    timeit_fast("pose fused DVL+accelerometer", lambda: ukf.predict_update2(0.0, None, pkg.POSE_VELOCITY, d["dvl"].data_ptr(),
+                                                                       syn.R_DVL, pkg.POSE_ACCELERATION, d["acc"].data_ptr(), syn.R_ACC,
+                                                                       memspace=pkg.DEVICE), B, P, ukf)
     if args.fast_only:
         if args.out:
             json.dump(res, open(args.out, "w"), indent=1)

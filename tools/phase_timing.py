@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--lib", default=LIB, help="another build of the library: only ms/step is reported when it has no probes")
+    ap.add_argument("--two-update", action="store_true", help="time the predict + DVL + accelerometer kernel (phases of both updates add up)")
     ap.add_argument("--mean-max-it", type=int, default=0, help="experiment: cap the iterated means (uwvkf_set_mean_policy)")
     ap.add_argument("--define", action="append", default=[], help="extra -D flags for --build (e.g. UWVKF_FUSED_MAX_WARPS=8)")
     args = ap.parse_args()
@@ -70,16 +71,20 @@ def main():
         ukf.set_mean_policy(1e-9, args.mean_max_it)
     _, cov0 = syn.pose_initial(cfg)
     CH = 1 << 16
-    gy, dv = [], []
+    gy, dv, ac = [], [], []
     for o in range(0, B, CH):
         idx = np.arange(o, min(o + CH, B))
         mu_c, _ = syn.pose_initial_batch(idx, cfg, with_cov=False)
         ukf.set_state(mu_c, cov0, first=o)
         i = syn.pose_inputs(idx, 1)
-        gy.append(i["gyro"]); dv.append(i["dvl"])
+        gy.append(i["gyro"]); dv.append(i["dvl"]); ac.append(i["acc"])
     gyro = torch.from_numpy(np.ascontiguousarray(np.concatenate(gy))).to(dev)
     dvl = torch.from_numpy(np.ascontiguousarray(np.concatenate(dv))).to(dev)
     step = lambda: ukf.predict_update(DT, gyro.data_ptr(), pkg.POSE_VELOCITY, dvl.data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
+    if args.two_update:
+        acc = torch.from_numpy(np.ascontiguousarray(np.concatenate(ac))).to(dev)
+        step = lambda: ukf.predict_update2(DT, gyro.data_ptr(), pkg.POSE_VELOCITY, dvl.data_ptr(), syn.R_DVL, pkg.POSE_ACCELERATION,
+                                           acc.data_ptr(), syn.R_ACC, memspace=pkg.DEVICE)
     out = np.zeros(40, dtype=np.uint64)
     for _ in range(3):
         step()
