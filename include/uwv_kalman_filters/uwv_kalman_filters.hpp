@@ -363,6 +363,19 @@ class PoseUKF : public FilterBase<UWVKF_POSE_DIM, UWVKF_POSE_DOF> {
                                   const double *aux = nullptr, const uint8_t *valid = nullptr) {
     detail::check(uwvkf_pose_predict_update(h_, delta_t, w, meas_kind, z, R, 0, aux, valid, UWVKF_HOST));
   }
+  // predictionStep + two updates (e.g. DVL + accelerometer, the 100 Hz step of a full PoseUKF) in one call
+  void predictionStepAndIntegrate2(double delta_t, const double *w, int kind_a, const double *z_a, const double *R_a, int kind_b,
+                                   const double *z_b, const double *R_b, const uint8_t *valid_a = nullptr,
+                                   const uint8_t *valid_b = nullptr) {
+    detail::check(uwvkf_pose_predict_update2(h_, delta_t, w, kind_a, z_a, R_a, valid_a, kind_b, z_b, R_b, valid_b, UWVKF_HOST));
+  }
+  // pipelined driver-loop step on HOST sample buffers (uwvkf_pose_step_host): rotation rate + predictionStep + integrateMeasurement,
+  // navigation solution [batch][10] back; see include/uwvkf.h for when the buffers may be reused.  synchronize() drains the pipeline.
+  void stepHost(double delta_t, const double *w_host, int meas_kind, const double *z_host, const double *R, double *nav_out_host,
+                const double *aux = nullptr) {
+    detail::check(uwvkf_pose_step_host(h_, delta_t, w_host, meas_kind, z_host, R, aux, nav_out_host));
+  }
+  void synchronize() { detail::check(uwvkf_synchronize(h_)); }
   void resetFilterWithExternalPose(const Affine3d &imu_in_nav) {   // reference src/PoseUKF.cpp:685-691
     double p[7] = {imu_in_nav.translation[0], imu_in_nav.translation[1], imu_in_nav.translation[2],
                    imu_in_nav.rotation.x, imu_in_nav.rotation.y, imu_in_nav.rotation.z, imu_in_nav.rotation.w};

@@ -200,6 +200,9 @@ struct FusedCfg {
 #ifndef UWVKF_ILV_UNCLAMPED       // 1: TrailStream addresses rows without the per-column clamp (no lane-dependent column offsets)
 #define UWVKF_ILV_UNCLAMPED 1
 #endif
+#ifndef UWVKF_LANE_PINNED         // 1: the lane index cannot be re-materialised from SR_TID inside the filter loop
+#define UWVKF_LANE_PINNED 0
+#endif
 #ifndef UWVKF_ILV_EARLY           // 1: request the first batches before the panel downdate instead of after it
 #define UWVKF_ILV_EARLY 0
 #endif
@@ -708,7 +711,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   extern __shared__ __align__(16) double smem[];
   double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
-  const int warp = threadIdx.x >> 5, lane_c = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int lane_c = threadIdx.x & 31;
+#if UWVKF_LANE_PINNED
+  // opaque ONCE, before the filter loop: the compiler may still hoist everything derived from the lane index out of the loop,
+  // but it can no longer re-materialise the index itself from SR_TID (40 S2R + LOP3 pairs in the loop body otherwise)
+  asm volatile("" : "+r"(lane_c));
+#endif
   int lane = lane_c;
   double *w = smem + C::CTA + warp * C::TOTAL;
   double *mu = w + C::O_MU, *S = w + C::O_S, *Lw = w + C::O_L, *G = w + C::O_G;
