@@ -28,8 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 DT = 0.01
 B_ALG = 23760.0          # algorithmic HBM bytes per filter-step: read + write of mu (54) and packed Sigma (1431) doubles
 W_ALG = 1.0e6            # FP64 flop per filter-step of the REFERENCE algorithm (symmetric-minimal count)
-W_EXEC = 1.508e5         # FP64 flop per filter-step the fused kernel executes (ncu: 32 x (2 DFMA + DMUL + DADD) + 512 per DMMA,
-                         # profiles/r1_v5_pose_fused_kernel_1M.txt): the prefix-structured transform does 7x less arithmetic
+W_EXEC = 1.518e5         # FP64 flop per filter-step the fused kernel executes (ncu: 32 x (2 x 1507 DFMA + 553 DMUL + 122 DADD) + 512 x
+                         # 66 DMMA, profiles/r2_pose_fused_kernel_1M.txt): the prefix-structured transform does 7x less arithmetic
 FP64_PEAK = 36.9e12      # measured DFMA peak of this pool's B200 (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)
 METRIC = "PoseUKF predict+update filter-steps/sec"
 UNIT = "filter-steps/s"

@@ -23,6 +23,9 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
+#ifndef UWVKF_SHRINK              // 1: predict kernels shrink the panel to 9 columns after the predict's factorisation (FusedCfg::KT): parity green, 2 % slower, off
+#define UWVKF_SHRINK 0
+#endif
 #ifndef UWVKF_TWO_BUF             // 1: kernels with a predict keep TWO [mu | panel] buffers per warp (incoming / working): parity green, 1.5 % slower, off
 #define UWVKF_TWO_BUF 0
 #endif
@@ -144,6 +147,15 @@ struct FusedCfg {
   static constexpr int KP = KP0 > KPM ? KP0 : KPM;                          // panel width
   static constexpr int PANEL = KP * N - (KP * (KP - 1)) / 2;                // doubles in the panel
   static constexpr int PANEL_E = ((PANEL + 1) / 2) * 2;
+  // Kernels with a predict need 15 columns for its factorisation, but columns 9..14 hold affine x affine entries only and
+  // have no coupled partner columns: past the predict they obey the elementwise expression of the trailing triangle.  When the
+  // update (if any) is content with 9 columns and reads no tail coordinates, the panel therefore SHRINKS to KT = 9 columns after
+  // the factorisation: the panel transform, the panel downdate and the write-back stop there, and the trailing pass starts at
+  // column 9, reading the old values of columns 9..14 from HBM (L2-hot: the prefix fetch has just pulled them through).
+  static constexpr int KU = (KM > KA ? KM : KA) > 9 ? (KM > KA ? KM : KA) : 9;
+  static constexpr bool SHRINK = UWVKF_SHRINK && HAS_PREDICT && NT == 0 && KPM == 0 && KIND2 == M_NONE && KU < KP;
+  static constexpr int KT = SHRINK ? KU : KP;                                // first column of the trailing pass
+  static constexpr int PANEL_T = KT * N - (KT * (KT - 1)) / 2;
   static constexpr int KL = KP;                                             // largest leading factor
   static constexpr int LSZ = ((KL * (KL | 1) + 1) / 2) * 2;        // square, odd column stride
   static constexpr int KE = ((KL + 1) / 2) * 2;
@@ -393,9 +405,10 @@ __device__ __forceinline__ Quat ori_transform_reg(double *G, const double (&a0)[
 // (new values into registers, one barrier, write), then the three velocity columns the same way, then every other column in
 // place.  Two barriers instead of six and no read-modify-write chains through shared memory.  Orientation rows and columns are
 // left alone (the caller overwrites them with the unscented transform).
-template <int KP>
+template <int KP>   // KP: columns to transform (>= 9: the coupled position / velocity groups are always inside)
 __device__ __forceinline__ void process_panel(double *S, const double *Qs, const double *ftab, const double (&f)[2], double dt, int lane,
                                               int colane) {
+  static_assert(KP >= 9, "the coupled column groups must be transformed here");
   const double dt2 = dt * dt;
   const bool rp = lane < 3 || (lane >= T_VEL && lane < T_ACC);   // row x0 = lane has a coupled partner (rows x1 never do)
   const int px = lane + (lane < 3 ? 6 : 3);
@@ -707,7 +720,8 @@ template <int HAS_PREDICT, int KIND, int WARPS, int KIND2 = M_NONE>
 __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
   using C = FusedCfg<HAS_PREDICT, KIND, KIND2>;
   constexpr int KCW = C::KCW;
-  constexpr int KP = C::KP, KE = C::KE;
+  constexpr int KP = C::KP, KT = C::KT, KE = C::KE;
+  static_assert(!C::TWO || !C::SHRINK, "the two-buffer variant transforms the whole panel");
   extern __shared__ __align__(16) double smem[];
   double *Qs = smem + C::C_Q;                        // dt^2 Q, packed (only when HAS_PREDICT)
   double *ftab = smem + C::C_FTAB, *mtau = smem + C::C_MTAU, *otab = smem + C::C_OTAB;
@@ -800,7 +814,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
     // prefix of the warp's next filter into L2 now; also fetch the small per-filter inputs early
     {
-      const char *tr = reinterpret_cast<const char *>(blk + OFF_S + C::PANEL);
+      const char *tr = reinterpret_cast<const char *>(blk + OFF_S + C::PANEL);   // (columns KT..KP-1 arrive with the prefix)
       constexpr int TB = (NP - C::PANEL) * 8;
 #if UWVKF_TRAIL_PREFETCH_L1
       for (int o = lane * 128; o < TB; o += 32 * 128) prefetch_l1(tr + o);
@@ -902,7 +916,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         PH(8);
 #if !UWVKF_EXP_SKIP_PANEL   // experiment switch (WRONG results; what the phase costs)
         if constexpr (C::TWO) process_panel_out<KP>(SA, S, Qs, ftab, rdf, dt, lane, colane);
-        else process_panel<KP>(S, Qs, ftab, rdf, dt, lane, colane);
+        else process_panel<C::KT>(S, Qs, ftab, rdf, dt, lane, colane);
 #endif
         PH(9);
         // orientation rows/cols: T F^T (+ Q cross terms)
@@ -1205,7 +1219,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           // the factorisation of apply_delta
           constexpr bool ILV = UWVKF_ILV && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY) && !DEFER;
           constexpr int M1_ = SECOND ? C::MF::M : M, M2_ = SECOND ? M : 0;   // the pass of a second update carries both downdates
-          TrailStream<HAS_PREDICT != 0, KP, M1_, UWVKF_ILV_UB, UWVKF_ILV_DEPTH, M2_> ts;
+          TrailStream<HAS_PREDICT != 0, KT, M1_, UWVKF_ILV_UB, UWVKF_ILV_DEPTH, M2_> ts;
           // Filters whose prediction was refused (rare) still run the batches -- no branch around loads whose values are consumed
           // several phases later -- but with every store predicated off; the classic pass then handles them
           const bool ilv = ILV && (HAS_PREDICT ? predicted : true);
@@ -1230,7 +1244,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #endif
           // panel downdate: Sigma[x][b] -= (KS)_x . K_b
 #pragma unroll
-          for (int b = 0; b < KP; ++b) {
+          for (int b = 0; b < KT; ++b) {
             const int cb = coloff(b);
             const double2 k01 = *reinterpret_cast<const double2 *>(KC + KCW * b + KOFF);
             const double k0 = k01.x, k1 = k01.y, k2 = KC[KCW * b + KOFF + 2];
@@ -1320,7 +1334,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             // the downdated covariance lost definiteness in its leading block: roll the panel back, drop the update
             st |= ST_NOT_SPD;
 #pragma unroll 1
-            for (int b = 0; b < KP; ++b) {
+            for (int b = 0; b < KT; ++b) {
               const int cb = coloff(b);
               const double k0 = KC[KCW * b + KOFF], k1 = KC[KCW * b + KOFF + 1], k2 = KC[KCW * b + KOFF + 2];
 #pragma unroll
@@ -1373,10 +1387,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         const double2 *src = reinterpret_cast<const double2 *>(mu);
         // if PANEL is odd the last double2 would also carry the first trailing entry, which the interleaved trailing pass
         // has already rewritten in HBM: the last panel entry goes out on its own
-        constexpr int NVW = (C::PANEL & 1) ? NV - 1 : NV;
+        constexpr int NVT = (56 + C::PANEL_T + 1) / 2;                 // [mu | the KT columns that are still panel]
+        constexpr int NVW = (C::PANEL_T & 1) ? NVT - 1 : NVT;
 #pragma unroll 4
         for (int k = lane; k < NVW; k += 32) __stcs(dst + k, src[k]);
-        if ((C::PANEL & 1) && lane == 0) __stcs(blk + 2 * NVW, mu[2 * NVW]);
+        if ((C::PANEL_T & 1) && lane == 0) __stcs(blk + 2 * NVW, mu[2 * NVW]);
       }
       __syncwarp();
       if constexpr (!C::TWO) {   // the panel buffer is free now: start the next filter's prefix, it lands during the trailing pass
@@ -1401,23 +1416,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       if (trailing_done || UWVKF_EXP_SKIPTRAIL) {
         // the interleaved pass (TrailStream) has already rewritten the trailing triangle
       } else if constexpr (KIND2 != M_NONE) {   // both downdates in one pass; refused updates carry zero factors
-        if (HAS_PREDICT && predicted) trailing_pass<true, true, KP, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
-        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
+        if (HAS_PREDICT && predicted) trailing_pass<true, true, KT, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
+        else trailing_pass<false, true, KT, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
       } else if constexpr (KIND == M_NONE) {
-        trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        trailing_pass<true, false, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       } else if constexpr (!HAS_PREDICT) {
-        trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        trailing_pass<false, true, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       } else if constexpr (UWVKF_ILV && UWVKF_COLD_CALL) {   // rare: the prediction or the update of this filter was refused
         if (predicted && updated)
-          trailing_pass_cold<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
+          trailing_pass_cold<true, true, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
         else if (predicted)
-          trailing_pass_cold<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
+          trailing_pass_cold<true, false, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
         else
-          trailing_pass_cold<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
+          trailing_pass_cold<false, true, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow[0], frow[1], ksr[0][0], ksr[0][1], ksr[0][2], ksr[1][0], ksr[1][1], ksr[1][2], q2add, tlane);
       } else {
-        if (predicted && updated) trailing_pass<true, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
-        else if (predicted) trailing_pass<true, false, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
-        else trailing_pass<false, true, KP, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        if (predicted && updated) trailing_pass<true, true, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        else if (predicted) trailing_pass<true, false, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
+        else trailing_pass<false, true, KT, MM_, TUB, TDEPTH>(gS, Qs, KC, frow, ksr, q2add, tlane);
       }
     }
     else if constexpr (!C::TWO) {
