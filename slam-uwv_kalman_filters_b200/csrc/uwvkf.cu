@@ -549,27 +549,30 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
   return UWVKF_OK;
 }
 
+static void destroy_pipe(uwvkf_handle h) {
+  auto *p = h->pipe;
+  if (!p) return;
+  if (p->s_in) cudaStreamSynchronize(p->s_in);
+  if (p->s_out) cudaStreamSynchronize(p->s_out);
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(p->d_w[k]); cudaFree(p->d_z[k]); cudaFree(p->d_nav[k]);
+    if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+    if (p->ev_main[k]) cudaEventDestroy(p->ev_main[k]);
+    if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
+  }
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  delete p;
+  h->pipe = nullptr;
+}
+
 int uwvkf_destroy(uwvkf_handle h) {
   if (!h) return UWVKF_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
   cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp); cudaFree(h->d_uwv);
   cudaFree(h->d_z2); cudaFree(h->d_valid2);
-  if (h->pipe) {
-    auto *p = h->pipe;
-    if (p->s_in) cudaStreamSynchronize(p->s_in);
-    if (p->s_out) cudaStreamSynchronize(p->s_out);
-    for (int k = 0; k < 2; ++k) {
-      cudaFree(p->d_w[k]); cudaFree(p->d_z[k]); cudaFree(p->d_nav[k]);
-      if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
-      if (p->ev_main[k]) cudaEventDestroy(p->ev_main[k]);
-      if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
-    }
-    if (p->s_in) cudaStreamDestroy(p->s_in);
-    if (p->s_out) cudaStreamDestroy(p->s_out);
-    delete p;
-    h->pipe = nullptr;
-  }
+  destroy_pipe(h);
   small_destroy(h);
   delete h;
   return UWVKF_OK;
@@ -579,8 +582,14 @@ int uwvkf_set_stream(uwvkf_handle h, void *s) {
   if (!h) return fail(UWVKF_ERR_INVALID_ARGUMENT, "null handle");
   if (h->capturing) return fail(UWVKF_ERR_INVALID_ARGUMENT, "cannot switch streams during a graph capture");
   CK(cudaSetDevice(h->device));
-  // staged inputs (d_z, d_tmp, ...) and kernels may still be in flight on the old stream: drain it before the switch
+  // staged inputs (d_z, d_tmp, ...) and kernels may still be in flight on the old stream: drain it before the switch (and
+  // the copy streams of the host-buffer pipeline, whose events refer to work on the old stream)
   CK(cudaStreamSynchronize(h->stream));
+  if (h->pipe) {
+    CK(cudaStreamSynchronize(h->pipe->s_in));
+    CK(cudaStreamSynchronize(h->pipe->s_out));
+    h->pipe->out_pending[0] = h->pipe->out_pending[1] = false;
+  }
   h->stream = (cudaStream_t)s;
   return UWVKF_OK;
 }
@@ -1090,7 +1099,12 @@ int uwvkf_pose_step_host(uwvkf_handle h, double dt, const double *w_host, int me
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_main[k], cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out[k], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) return fail(UWVKF_ERR_CUDA, std::string("pipeline allocation failed: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {   // leave no half-built pipeline behind: the next call starts over
+      const std::string msg = cudaGetErrorString(e);
+      cudaGetLastError();
+      destroy_pipe(h);
+      return fail(UWVKF_ERR_CUDA, "pipeline allocation failed: " + msg);
+    }
   }
   auto *p = h->pipe;
   const int slot = (int)(p->calls & 1);

@@ -177,3 +177,25 @@ def test_bottom_matches_committed_golden_sequence(pkg, syn):
         gmu, gcov = ukf.get_state()
         check(gmu, gcov, g[s][:, :4], g[s][:, 4:].reshape(B, 3, 3), f"bottom golden step {s}")
     ukf.close()
+
+
+def test_list_arguments_do_not_alias(pkg, syn):
+    """integrate_range(z, R, [0, 0, 1], [0, 0, 0]): the two converted list temporaries used to share one freed buffer, so the
+    beam direction silently became the origin (advisor finding).  Lists, tuples and float32 arrays must behave like float64 arrays."""
+    B = 16
+    filt = np.arange(B)
+    mu, cov = syn.bottom_initial_batch(filt)
+    a, b = pkg.BottomUKFBatch(B), pkg.BottomUKFBatch(B)
+    a.set_state(mu, cov); b.set_state(mu, cov)
+    z = syn.bottom_inputs(filt, 1)["ranges"][:, 0].copy()
+    direction, origin = [0.0, 0.0, -1.0], [0.1, -0.2, 0.3]
+    a.integrate_range(z.astype(np.float32), 4e-4, direction, tuple(origin))
+    b.integrate_range(z.astype(np.float32).astype(np.float64), np.array([4e-4]), np.array(direction), np.array(origin))
+    ma, ca = a.get_state()
+    mb, cb = b.get_state()
+    assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    assert not np.array_equal(ma, mu)
+    om, oc, st = orc.bottom_update_range(mu[0], cov[0], z[:1].astype(np.float32).astype(np.float64), np.array([4e-4]), np.array(direction),
+                                         np.array(origin))
+    check(ma[:1], ca[:1], om[None], oc[None], "range update from list arguments")
+    a.close(); b.close()
