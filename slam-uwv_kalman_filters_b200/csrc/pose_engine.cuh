@@ -97,6 +97,24 @@ struct WL {
   static constexpr int TOTAL = F + 56;
 };
 
+// Layout of the STREAMED dense update (pose_efforts_kernel): the covariance is not resident.  The factorisation reads it from
+// global memory, the rank-6 downdate streams it HBM -> registers -> HBM, and only the six leading columns -- what apply_delta
+// works on, a prefix of the packed array -- live in shared memory.  23.6 KB per warp instead of 32.6: 9 warps per SM instead of 6.
+struct WLS {
+  static constexpr int MG = MAXM;
+  static constexpr int S6 = 304;            // 6 leading columns: 6 * 53 - 15 = 303 entries
+  static constexpr int LSZ = 1432;          // 53 x 48 panel factor, column-packed with N rows per column
+  static constexpr int KE = 54;
+  static constexpr int L = OFF_S + S6;
+  static constexpr int INVD = L + LSZ;
+  static constexpr int G = INVD + KE;
+  static constexpr int T = G + MG * KE;
+  static constexpr int KS = T + MG * 56;
+  static constexpr int DL = KS + MG * 56;
+  static constexpr int F = DL + 56;
+  static constexpr int TOTAL = F + 56;
+};
+
 // ------------------------------------------------------------------------------------------------------
 // entry (i, j), i >= j, of a lower triangle packed by columns with R rows per column
 template <int R>
@@ -110,9 +128,26 @@ __device__ __forceinline__ int lidxr(int i, int j) { return j * R - ((j * (j - 1
 // (47 % of all instructions of the body-efforts update, 70 % of the visual-marker update).  The 4 x 4 diagonal block is then
 // factorised column by column with the pivots and multipliers travelling by shuffle.  The summation order per entry is the
 // sequential one (k ascending).  The factor is stored column-packed with R rows per column (lidxr<R>).
-template <int K, int R, int SN, bool FAST>
+// SRCPIPE: the source lives in global memory (streamed dense update): the entries of block jb + 4 are requested before the
+// k-loop of block jb runs, so their latency hides behind it.
+template <int K, int R, int SN, bool FAST, bool SRCPIPE = false>
 __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double *invd, int lane) {
   bool ok = true;
+  double nxt[2][4];      // SRCPIPE: source entries of the next block (rows jb' + lane, jb' + lane + 32)
+  (void)nxt;
+  auto fetch = [&](int jb, double (&dst)[2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = jb + lane + 32 * h;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cc = jb + c < K ? jb + c : K - 1;                       // (clamped: the tail block is narrower)
+        const int ii = (i >= cc && i < R) ? i : cc;                       // in-range address for lanes without an entry
+        dst[h][c] = S[lidxr<SN>(ii, cc)];
+      }
+    }
+  };
+  if constexpr (SRCPIPE) fetch(0, nxt);
   // Rows are dealt out RELATIVE to the block: lane l works on rows jb + l (and jb + l + 32 while the block still has more than 32
   // rows below its top), so no lane idles on rows above the block, the second round disappears for the later blocks, and the
   // pivot row jb + c always sits on lane c.
@@ -123,7 +158,13 @@ __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double
     for (int h = 0; h < RND; ++h) {
       const int i = jb + lane + 32 * h;
 #pragma unroll
-      for (int c = 0; c < BW; ++c) acc[h][c] = (i >= jb + c && i < R) ? S[lidxr<SN>(i, jb + c)] : 0.0;
+      for (int c = 0; c < BW; ++c) {
+        if constexpr (SRCPIPE) acc[h][c] = (i >= jb + c && i < R) ? nxt[h][c] : 0.0;
+        else acc[h][c] = (i >= jb + c && i < R) ? S[lidxr<SN>(i, jb + c)] : 0.0;
+      }
+    }
+    if constexpr (SRCPIPE) {
+      if (jb + 4 < K) fetch(jb + 4, nxt);
     }
     int cb = 0;                       // lidxr<R>(0, k) - k: Lw[cb + i] = L[i][k]
 #pragma unroll 2
@@ -180,7 +221,7 @@ __device__ __forceinline__ bool chol_blocked(const double *S, double *Lw, double
 // column entries travel by shuffles (no shared-memory round trips inside the recurrence).
 // R > K (general path only): the factorisation is carried over R rows -- the first K columns of the factor of the leading
 // R x R block, i.e. the PANEL FACTOR Sigma[0:R, 0:K] L11^-T -- stored column-packed with R rows per column (lidxr<R>).
-template <int K, int R = K>
+template <int K, int R = K, bool SRCPIPE = false>
 __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double *invd, int lane) {
   static_assert(R == K || K > 32, "extra rows only in the general path");
   if constexpr (K <= 32) {
@@ -209,7 +250,7 @@ __device__ __forceinline__ bool chol_leading(const double *S, double *Lw, double
     return ok;
   } else {
     // general path (K up to N): blocked left-looking factorisation, lanes own rows (chol_blocked)
-    return chol_blocked<K, R, N, false>(S, Lw, invd, lane);
+    return chol_blocked<K, R, N, false, SRCPIPE>(S, Lw, invd, lane);
   }
 }
 
@@ -337,10 +378,9 @@ __device__ __forceinline__ Quat so3_mean(const Quat (&qp)[ROUNDS], const double 
 
 // Unscented transform of the orientation rows with the leading-K sigma points qp (one round, K <= 15):
 // returns the new mean quaternion, writes Sigma_oo (6 values) and T = (A L^-1) Sigma[0:K,:] (3 x N).
-template <int K, int KMAX>
+template <int K, int KMAX, class W = WL<KMAX>>
 __device__ __forceinline__ Quat ori_transform(double *w, const Quat &qp, int p, const Params &P, double soo[6], int lane,
                                               unsigned &status) {
-  using W = WL<KMAX>;
   double *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *G = w + W::G, *T = w + W::T;
   const bool act = p < 2 * K + 1;
   const bool on = act && p > 0;
@@ -526,9 +566,8 @@ __device__ __forceinline__ bool predict(double *w, const double *Qs, const uint1
 }
 
 // ukfom apply_delta(delta): only the orientation (tangent 3..5, prefix 6) is a non-vector component.
-template <int KMAX>
+template <int KMAX, class W = WL<KMAX>>
 __device__ __forceinline__ bool apply_delta(double *w, const Params &P, int lane, unsigned &status) {
-  using W = WL<KMAX>;
   constexpr int K = 6;
   double *mu = w + OFF_MU, *S = w + OFF_S, *Lw = w + W::L, *invd = w + W::INVD, *T = w + W::T, *dl = w + W::DL;
   if (!chol_leading<K>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
@@ -540,7 +579,7 @@ __device__ __forceinline__ bool apply_delta(double *w, const Params &P, int lane
   auto d = [&](int t) { return (on && t >= j) ? sg * Lw[lidx<K>(t, j)] : 0.0; };
   Quat qp = so3_boxplus(q, Vec3{dl[3] + d(3), dl[4] + d(4), dl[5] + d(5)}, 1.0);
   double soo[6];
-  Quat r = ori_transform<K, KMAX>(w, qp, p, P, soo, lane, status);
+  Quat r = ori_transform<K, KMAX, W>(w, qp, p, P, soo, lane, status);
   for (int x = lane; x < N; x += 32) {
     if (x >= 3 && x < 6) continue;
 #pragma unroll
@@ -774,10 +813,13 @@ __device__ __forceinline__ void sym_inverse(const double *S, double *Si) {
 
 // ukfom update(z, h, R, gate) for a vector measurement (reference call sites src/PoseUKF.cpp:479-610).
 // gate95: the reference's d2p95 (src/PoseUKF.cpp:275-286), otherwise accept_any.
-template <int KIND, int KMAX>
+// gSig != nullptr (STREAMED form, layout WLS): the covariance lives in global memory at gSig (packed); the shared-memory S
+// holds its six leading columns only, filled -- downdated -- by the streaming pass before apply_delta runs.
+template <int KIND, int KMAX, class W = WL<KMAX>>
 __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const double *z, const double *Rm, const double *aux,
-                                       bool gate95, const Params &P, int lane, unsigned &status, const double *model = nullptr) {
-  using W = WL<KMAX>;
+                                       bool gate95, const Params &P, int lane, unsigned &status, const double *model = nullptr,
+                                       double *gSig = nullptr) {
+  constexpr bool STREAM = std::is_same<W, WLS>::value;
   using MM = Meas<KIND>;
   constexpr int K = MM::K, M = MM::M;
   static_assert(K <= KMAX, "kernel instantiated with too small a panel");
@@ -788,7 +830,8 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
   // cross-covariance is a product with the panel factor (no triangular solve, no G Sigma)
   constexpr bool PANELF = (K > 32) && (KMAX >= N);
   constexpr int R = PANELF ? N : K;
-  if (!chol_leading<K, R>(S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
+  static_assert(!STREAM || PANELF, "the streamed form carries the panel factor");
+  if (!chol_leading<K, R, STREAM>(STREAM ? gSig : S, Lw, invd, lane)) { status |= ST_NOT_SPD; return false; }
   // sigma points through the measurement model
   double Z[ROUNDS][M], wt[ROUNDS];
 #pragma unroll
@@ -893,45 +936,96 @@ __device__ __forceinline__ bool update(double *w, const uint16_t *lut, const dou
   }
   __syncwarp();
   // Sigma -= (K S) K^T
-  for (int e = lane; e < NP; e += 32) {
-    unsigned ij = lut[e];
-    int i = ij & 0xff, jj = ij >> 8;
-    double s = S[e];
+  // STREAMED form: columns [b0, b1) of the packed covariance are read from HBM; rows x0 = lane, x1 = lane + 32 keep their (K S)
+  // factors in registers and column b contributes K_b by M broadcast loads.  Columns 0..5 go to the shared-memory panel (all
+  // that apply_delta works on), the others straight back to HBM -- but only once apply_delta has succeeded, so that a refused
+  // update leaves the filter bit-identical in memory.
+  auto stream_downdate = [&](int b0, int b1) {
+    double ksx[2][M];
 #pragma unroll
-    for (int c = 0; c < M; ++c) s = fma(-KS[c * 56 + i], T[c * 56 + jj], s);
-    S[e] = s;
+    for (int h = 0; h < 2; ++h) {
+      const int x = lane + 32 * h;
+#pragma unroll
+      for (int c = 0; c < M; ++c) ksx[h][c] = x < N ? KS[c * 56 + x] : 0.0;
+    }
+#pragma unroll 8
+    for (int b = b0; b < b1; ++b) {
+      double kb[M];
+#pragma unroll
+      for (int c = 0; c < M; ++c) kb[c] = T[c * 56 + b];
+      const int cb = cidx(b, b) - b;   // cidx(x, b) = cb + x
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = lane + 32 * h;
+        if (x >= b && x < N) {
+          double sv = gSig[cb + x];
+#pragma unroll
+          for (int c = 0; c < M; ++c) sv = fma(-ksx[h][c], kb[c], sv);
+          if (b < 6) S[cb + x] = sv; else gSig[cb + x] = sv;
+        }
+      }
+    }
+    __syncwarp();
+  };
+  if constexpr (STREAM) {
+    stream_downdate(0, 6);
+  } else {
+    for (int e = lane; e < NP; e += 32) {
+      unsigned ij = lut[e];
+      int i = ij & 0xff, jj = ij >> 8;
+      double s = S[e];
+#pragma unroll
+      for (int c = 0; c < M; ++c) s = fma(-KS[c * 56 + i], T[c * 56 + jj], s);
+      S[e] = s;
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  // T is overwritten by apply_delta; keep K in registers for a possible rollback
-  double kr[2][M], ksr[2][M];
+  // apply_delta reuses the first three rows of T (its 3 x N cross-covariance); those rows of K are kept in registers for the
+  // pass that follows (rollback, or the streamed rest of the downdate).  K S and the other rows of K stay where they are.
+  constexpr int MK = M < 3 ? M : 3;
+  double kr[2][MK];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     int x = lane + 32 * h;
 #pragma unroll
-    for (int a = 0; a < M; ++a) { kr[h][a] = x < N ? T[a * 56 + x] : 0.0; ksr[h][a] = x < N ? KS[a * 56 + x] : 0.0; }
+    for (int a = 0; a < MK; ++a) kr[h][a] = x < N ? T[a * 56 + x] : 0.0;
   }
   __syncwarp();
-  if (!apply_delta<KMAX>(w, P, lane, status)) {
+  if (!apply_delta<KMAX, W>(w, P, lane, status)) {
     // downdated Sigma lost definiteness in its leading block: roll the downdate back, leave the filter as it was
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       int x = lane + 32 * h;
       if (x < N) {
 #pragma unroll
-        for (int a = 0; a < M; ++a) { T[a * 56 + x] = kr[h][a]; KS[a * 56 + x] = ksr[h][a]; }
+        for (int a = 0; a < MK; ++a) T[a * 56 + x] = kr[h][a];
       }
     }
     __syncwarp();
-    for (int e = lane; e < NP; e += 32) {
-      unsigned ij = lut[e];
-      int i = ij & 0xff, jj = ij >> 8;
-      double s = S[e];
+    if constexpr (!STREAM) {   // (streamed form: nothing has been written to HBM yet, the panel copy is simply dropped)
+      for (int e = lane; e < NP; e += 32) {
+        unsigned ij = lut[e];
+        int i = ij & 0xff, jj = ij >> 8;
+        double s = S[e];
 #pragma unroll
-      for (int c = 0; c < M; ++c) s = fma(KS[c * 56 + i], T[c * 56 + jj], s);
-      S[e] = s;
+        for (int c = 0; c < M; ++c) s = fma(KS[c * 56 + i], T[c * 56 + jj], s);
+        S[e] = s;
+      }
+      __syncwarp();
+    }
+    return false;
+  }
+  if constexpr (STREAM) {   // accepted: the gain tables back from the registers (apply_delta reused T), then the rest of Sigma
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int x = lane + 32 * h;
+      if (x < N) {
+#pragma unroll
+        for (int a = 0; a < MK; ++a) T[a * 56 + x] = kr[h][a];
+      }
     }
     __syncwarp();
-    return false;
+    stream_downdate(6, N);
   }
   return true;
 }

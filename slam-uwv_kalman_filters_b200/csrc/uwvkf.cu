@@ -122,6 +122,50 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_step_kernel(pose::Launch a
   }
 }
 
+// Body-efforts update (measurementEfforts, reference src/PoseUKF.cpp:153-196, 581-602) in STREAMED form (pose::WLS): the
+// covariance stays in HBM -- read by the factorisation, streamed through registers by the rank-6 downdate -- and only mu and the
+// six leading columns live in shared memory: 8 warps per SM at 255 registers instead of 6.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) pose_efforts_kernel(pose::Launch a, const __grid_constant__ pose::Params P) {
+  using W = pose::WLS;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *w = smem + warp * W::TOTAL;
+  const pose::Op &op = a.ops[0];
+  constexpr int M = 6;
+  constexpr int NWB = pose::OFF_S + 303;          // mu (+ pad) and the six leading columns: what goes back from shared memory
+  for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.B; f += (long long)gridDim.x * WARPS) {
+    double *blk = a.state + f * pose::BLK;
+    __syncwarp();
+    // the whole block into L2 now: the factorisation and the streamed downdate read it from there
+    for (int o = lane * 128; o < pose::BLK * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(blk) + o));
+    for (int k = lane; k < pose::OFF_S; k += 32) w[k] = blk[k];
+    __syncwarp();
+    unsigned st = 0;
+    bool go = !(op.valid && !op.valid[f]);
+    double z[M], R[M * M];
+    if (go) {
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < M; ++k) { z[k] = op.z[f * M + k]; bad |= isnan(z[k]); }
+#pragma unroll
+      for (int k = 0; k < M * M; ++k) { R[k] = op.R[k]; bad |= isnan(R[k]); }
+      if (bad) { st |= pose::ST_NAN_MEAS; go = false; }
+    }
+    if (go) {
+      double *ctx = w + W::F;   // the context is evaluated at the mean, once per filter (reference src/PoseUKF.cpp:585-598)
+      pose::efforts_context(w, a.rot_rate + f * 3, P, ctx);
+      __syncwarp();
+      const bool dirty = pose::update<pose::M_BODY_EFFORTS, 53, W>(w, nullptr, z, R, ctx, false, P, lane, st, a.uwv, blk + pose::OFF_S);
+      __syncwarp();
+      if (dirty) {
+        for (int k = lane; k < NWB; k += 32) __stcs(blk + k, w[k]);
+      }
+    }
+    if (st && lane == 0) a.status[f] |= st;
+  }
+}
+
 // host (mu[count][54], cov[count][53*53] or one shared cov) -> device blocks, and the Markov offsets
 __global__ void pose_pack_kernel(const double *mu, const double *cov, long long cov_stride, double *state, double *offsets,
                                  long long first, long long count) {
@@ -280,6 +324,12 @@ namespace {
 #ifndef UWVKF_FUSED2
 #define UWVKF_FUSED2 0
 #endif
+// 1: the full body-efforts update runs in pose_efforts_kernel (covariance streamed from HBM instead of resident in shared memory:
+// 8 warps per SM instead of 6).  Parity green; 3.79 ms against 3.52 ms per 65,536 filters for the resident kernel -- the global
+// loads of the factorisation and of the streamed downdate cost more than the two extra warps bring.  Off.
+#ifndef UWVKF_EFFORTS_STREAMED
+#define UWVKF_EFFORTS_STREAMED 0
+#endif
 #ifndef UWVKF_FUSED2_WARPS
 #define UWVKF_FUSED2_WARPS 12
 #endif
@@ -435,6 +485,23 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
       return launch_fused<0, pose::M_VELOCITY, pose::M_ACCELERATION>(h, L);
 #endif
   }
+#if UWVKF_EFFORTS_STREAMED
+  // the full body-efforts update: streamed dense kernel (covariance in HBM, 8 warps per SM)
+  if (!force_v1 && dense_only && full_efforts && nops == 1 && !ops[0].Rdev) {
+    constexpr int WARPS = 8;
+    const size_t smem = (size_t)WARPS * pose::WLS::TOTAL * sizeof(double);
+    static unsigned long long attr_set = 0;   // one bit per device
+    if (!(attr_set >> h->device & 1ull)) {
+      CK(cudaFuncSetAttribute(pose_efforts_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set |= 1ull << h->device;
+    }
+    const int grid = (int)std::min<long long>((L.B + WARPS - 1) / WARPS, h->sm_count);
+    pose_efforts_kernel<WARPS><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
+    CK(cudaGetLastError());
+    h->launches++;
+    return UWVKF_OK;
+  }
+#endif
   // the velocity-only body-efforts update reads prefix 9 only: prefix-19 engine with six-row tables, 10 warps per SM
   if (!force_v1 && dense_only && !full_efforts && nops == 1) return launch_pose<20, kEffortsVelWarps>(h, L);
   return slow ? launch_pose<53, kSlowWarps>(h, L) : launch_pose<19, kFastWarps>(h, L);
