@@ -221,6 +221,9 @@ struct FusedCfg {
 #ifndef UWVKF_ILV_UPDATE_ONLY     // 1: the update-only kernels interleave their trailing pass as well
 #define UWVKF_ILV_UPDATE_ONLY 1
 #endif
+#ifndef UWVKF_ILV_PREDICT         // 1: the predict-only kernel interleaves its trailing pass with the predict's own phases: parity green, 4 % slower (spills), off
+#define UWVKF_ILV_PREDICT 0
+#endif
 #ifndef UWVKF_ILV_UB
 #define UWVKF_ILV_UB 8
 #define UWVKF_ILV_DEPTH 2
@@ -628,7 +631,7 @@ struct TrailStream {
       sv = fma(fr * c2f.y, sv, Qs[coloff(b) + row]);
       if (b >= T_WV && b < T_BADCP && row == b) sv += q2add;
     }
-    sv = fma(-k0, c01.x, sv);
+    if (M > 0) sv = fma(-k0, c01.x, sv);   // M == 0: process map only (predict-only kernel)
     if (M > 1) sv = fma(-k1, c01.y, sv);
     if (M > 2) sv = fma(-k2, c2f.x, sv);
     if constexpr (M2 > 0) {   // downdate of the second update: K2 in slots 4..6 of the column table, (K2 S2) rows j0..j2
@@ -879,7 +882,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         }
         PH(2);
         double soo[6], T[2][3];
-        Quat r = ori_transform_reg<K>(G, a0, a1, qp, p, P, soo, T, lane, st PH_ARG(3));
+        add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
+        // predict-only kernel: the trailing pass (process map only) needs nothing the predict computes, so its batches are
+        // interleaved with the sigma-point / mean / panel phases below, like the update kernels do inside apply_delta
+        constexpr bool PILV = UWVKF_ILV && UWVKF_ILV_PREDICT && KIND == M_NONE;
+        TrailStream<true, KP, 0, UWVKF_ILV_UB, UWVKF_ILV_DEPTH> pts;
+        double *const pgS = blk + OFF_S;
+        const double pq2 = dt2 * add;
+        auto pts_step = [&](auto i_) {
+          constexpr int I = decltype(i_)::value;
+          pts.template finish<I>(true, pgS, Qs, KC, frow, ksr, pq2, lane);
+          pts.template load<I + UWVKF_ILV_DEPTH>(pgS, lane);
+        };
+        if constexpr (PILV) {
+          pts.template load<0>(pgS, lane);
+          if (UWVKF_ILV_DEPTH > 1) pts.template load<1>(pgS, lane);
+          pts.load_secondary(pgS, lane);
+        }
+        Quat r;
+        if constexpr (PILV) {
+          r = so3_mean_lane(qp, ori_weight(p, K), P.mean_tol, P.mean_max_it, st);
+          pts.finish_secondary(true, pgS, Qs, KC, frow, ksr, pq2, lane);
+          pts_step(std::integral_constant<int, 0>{});
+          ori_deviations<K>(G, qp, r, p, soo);
+          pts_step(std::integral_constant<int, 1>{});
+          a_times_panel<K, 3>(G, a0, a1, T);
+          pts_step(std::integral_constant<int, 2>{});
+        } else {
+          r = ori_transform_reg<K>(G, a0, a1, qp, p, P, soo, T, lane, st PH_ARG(3));
+        }
         // effective process noise pieces (reference src/PoseUKF.cpp:448-460)
         double qoo[6];
         {
@@ -896,7 +927,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           auto rq = [&](int i, int b) { return t[i * 3] * Rm[b * 3] + t[i * 3 + 1] * Rm[b * 3 + 1] + t[i * 3 + 2] * Rm[b * 3 + 2]; };
           qoo[0] = rq(0, 0); qoo[1] = rq(1, 0); qoo[2] = rq(2, 0); qoo[3] = rq(1, 1); qoo[4] = rq(2, 1); qoo[5] = rq(2, 2);
         }
-        add = P.wv_scale * (vel.x * vel.x + vel.y * vel.y + 100.0 * vel.z * vel.z) * dt;
         const double (&rdf)[2] = frow;
         // new mean of the affine components: x + dt * rate, rate = v | a | (-1/tau)(x - offset)   (src/PoseUKF.cpp:25-78)
         // (branch-free: the three cases sit on different lanes of the same warp)
@@ -919,6 +949,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         else process_panel<C::KT>(S, Qs, ftab, rdf, dt, lane, colane);
 #endif
         PH(9);
+        if constexpr (PILV) pts_step(std::integral_constant<int, 3>{});
         // orientation rows/cols: T F^T (+ Q cross terms)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -945,6 +976,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
         if (x1 < DIM) mu[x1] = nm1;
         if (lane == 0) { mu[P_ORI] = r.x; mu[P_ORI + 1] = r.y; mu[P_ORI + 2] = r.z; mu[P_ORI + 3] = r.w; }
         predicted = true;
+        if constexpr (PILV) {
+          pts_step(std::integral_constant<int, 4>{}); pts_step(std::integral_constant<int, 5>{});
+          pts_step(std::integral_constant<int, 6>{}); pts_step(std::integral_constant<int, 7>{});
+          static_assert(decltype(pts)::NB <= 8, "drain more batches");
+          trailing_done = true;
+        }
         __syncwarp();
         PH(10);
       } else {
