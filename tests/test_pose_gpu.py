@@ -156,6 +156,101 @@ def test_fused_step_equals_separate_calls(pkg, syn, scen):
     a.close(); b.close()
 
 
+def _random_states(syn, scen, B, seed):
+    """Random filters far from the synthetic scenario: arbitrary attitudes, dense SPD covariances with the scales of a working
+    filter (Sigma = D C D with a random correlation matrix C of moderate condition number), perturbed parameter states."""
+    rng = np.random.default_rng(seed)
+    mu0, cov0 = syn.pose_initial(scen["cfg"])
+    sd = np.sqrt(np.diag(cov0))
+    mu = np.tile(mu0, (B, 1))
+    mu[:, 0:3] += rng.normal(size=(B, 3)) * [50.0, 50.0, 5.0]
+    q = rng.normal(size=(B, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    mu[:, 3:7] = q
+    mu[:, 7:10] = rng.normal(size=(B, 3)) * 0.5
+    mu[:, 10:13] = rng.normal(size=(B, 3)) * 0.2
+    mu[:, 13:19] += rng.normal(size=(B, 6)) * 1e-3
+    mu[:, 20:47] *= 1.0 + 0.05 * rng.normal(size=(B, 27))
+    mu[:, 47:53] = rng.normal(size=(B, 6)) * 0.1
+    cov = np.empty((B, 53, 53))
+    for f in range(B):
+        A = rng.normal(size=(53, 80))
+        Cm = A @ A.T / 80.0                                   # random correlation structure, condition number ~ 30
+        dg = np.sqrt(np.diag(Cm))
+        Cm = Cm / np.outer(dg, dg)
+        scale = sd * np.exp(0.5 * rng.normal(size=53))
+        cov[f] = Cm * np.outer(scale, scale)
+    off = np.concatenate([mu[:, 20:47], mu[:, 53:54]], axis=1)
+    return mu, cov, off, rng
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_states_parity(pkg, syn, scen, seed):
+    """Parity on RANDOM states (not the synthetic trajectory): predict, every vector update, the fused forms."""
+    B = 24
+    mu, cov, off, rng = _random_states(syn, scen, B, seed)
+    ukf = pkg.PoseUKFBatch(B, scen["par"])
+    ukf.set_process_noise(scen["Q"])
+    ukf.set_state(mu, cov)
+    ukf.set_offsets(off)
+    w = rng.normal(size=(B, 3)) * 0.2
+    ukf.integrate_rotation_rate(w)
+    # predict
+    ukf.prediction_step(DT)
+    gmu, gcov = ukf.get_state()
+    omu, ocov = oracle_predict(mu, cov, scen, w, off)
+    assert_parity(gmu, gcov, omu, ocov, f"random predict (seed {seed})")
+    # every vector update from the predicted state, each from the same start
+    import structured_ref as sr
+
+    def h_mean(name, m_, aux):   # the measurement model at the mean: where a plausible sample lies
+        q, p, v = m_[3:7], m_[0:3], m_[7:10]
+        if name == "velocity":
+            return sr.qrot(sr.qconj(q), v)
+        if name == "acceleration":
+            return sr.qrot(sr.qconj(q), m_[10:13] + np.array([0.0, 0.0, m_[19]])) + m_[16:19]
+        if name == "xy":
+            return p[0:2].copy()
+        if name == "z":
+            return p[2:3].copy()
+        if name == "pressure":
+            return np.array([syn.P_ATM - (p + sr.qrot(q, aux))[2] * m_[19] * m_[53]])
+        wgt = aux[0]
+        wv, wvb = np.array([m_[47], m_[48], 0.0]), np.array([m_[49], m_[50], 0.0])
+        return (wgt * sr.qrot(sr.qconj(q), v - wvb) + (1 - wgt) * sr.qrot(sr.qconj(q), v - wv))[0:2] + m_[51:53]
+
+    kinds = {
+        "velocity": (pkg.POSE_VELOCITY, orc.VELOCITY, 3, syn.R_DVL, None),
+        "acceleration": (pkg.POSE_ACCELERATION, orc.ACCELERATION, 3, syn.R_ACC, None),
+        "xy": (pkg.POSE_XY, orc.XY, 2, np.array([[0.04, 0.01], [0.01, 0.09]]), None),
+        "z": (pkg.POSE_Z, orc.Z, 1, np.array([[0.0025]]), None),
+        "pressure": (pkg.POSE_PRESSURE, orc.PRESSURE, 1, syn.R_PRESSURE, np.array([0.3, -0.1, 0.2])),
+        "adcp": (pkg.POSE_WATER_VELOCITY, orc.WATER_VELOCITY, 2, syn.R_ADCP, np.array([0.4])),
+    }
+    for name, (gk, ok, m, R, aux) in kinds.items():
+        ukf.set_state(omu, ocov)
+        ukf.clear_status()
+        zc = np.stack([h_mean(name, omu[f], aux) for f in range(B)])
+        z = np.ascontiguousarray(zc + rng.normal(size=(B, m)) * np.sqrt(np.diag(R)))
+        ukf.integrate_measurement(gk, z, R, aux=aux)
+        g2, c2 = ukf.get_state()
+        o2, oc2, sts = oracle_update(ok, omu, ocov, scen, z, R, aux, w)
+        gst = ukf.get_status()
+        assert np.array_equal(gst & 4 != 0, sts & 4 != 0), f"{name}: gate decisions differ"
+        assert not (gst & ~np.uint32(4)).any(), name
+        assert_parity(g2, c2, o2, oc2, f"random update {name} (seed {seed})")
+    # fused predict + DVL from the random start
+    ukf.set_state(mu, cov)
+    ukf.clear_status()
+    zc = np.stack([h_mean("velocity", omu[f], None) for f in range(B)])
+    z = np.ascontiguousarray(zc + 0.01 * rng.normal(size=(B, 3)))
+    ukf.predict_update(DT, w, pkg.POSE_VELOCITY, z, syn.R_DVL)
+    g3, c3 = ukf.get_state()
+    o3, oc3, _ = oracle_update(orc.VELOCITY, omu, ocov, scen, z, syn.R_DVL, None, w)
+    assert_parity(g3, c3, o3, oc3, f"random fused predict + DVL (seed {seed})")
+    assert not ukf.get_status().any()
+    ukf.close()
+
+
 def test_two_update_step_equals_separate_calls(pkg, syn, scen):
     """predictionStep + DVL + accelerometer in ONE kernel (uwvkf_pose_predict_update2) is bit-identical to the three separate
     calls -- also with dropout masks on either update, without a prediction (dt = 0), and for a pair that is not fused."""
