@@ -354,16 +354,6 @@ __device__ __forceinline__ Quat so3_mean_lane(const Quat &qp, double wt, double 
   return r;
 }
 
-// v[i] for a lane-dependent i without turning v into a local-memory array (shared memory takes most of the L1 here, so
-// local-memory traffic is served at L2 latency)
-__device__ __forceinline__ double pick6(const double (&v)[6], int i) {
-  double r = v[0];
-#pragma unroll
-  for (int k = 1; k < 6; ++k) r = (i == k) ? v[k] : r;
-  return r;
-}
-
-// Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh); T stays in registers.
 // Unscented transform of the orientation rows (see ori_transform in pose_engine.cuh) in three parts, so that a caller can slot
 // independent work between them (apply_delta interleaves batches of the trailing pass): the iterated mean, the deviations with
 // S_oo and A (to shared memory), and T = A Lp^T from the panel-factor rows in registers.
@@ -967,10 +957,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
             }
           }
         }
-        if (lane < 6) {
-          int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
-          int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-          S[cidx(3 + bi, 3 + bj)] = pick6(soo, lane) + pick6(qoo, lane);
+        if (lane == 0) {   // soo / qoo are warp-uniform: one lane stores the six entries (order: (3,3) (4,3) (5,3) (4,4) (5,4) (5,5))
+          S[cidx(3, 3)] = soo[0] + qoo[0]; S[cidx(4, 3)] = soo[1] + qoo[1]; S[cidx(5, 3)] = soo[2] + qoo[2];
+          S[cidx(4, 4)] = soo[3] + qoo[3]; S[cidx(5, 4)] = soo[4] + qoo[4]; S[cidx(5, 5)] = soo[5] + qoo[5];
         }
         if (x0 < P_ORI || x0 >= P_VEL) mu[x0] = nm0;
         if (x1 < DIM) mu[x1] = nm1;
@@ -1346,10 +1335,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
                 for (int c = 0; c < 3; ++c) S[x < 3 ? (coloff(x) + 3 + c) : (coloff(3 + c) + x)] = TA[h][c];
               }
             }
-            if (lane < 6) {
-              int bi = (lane < 3) ? lane : (lane < 5 ? lane - 2 : 2);
-              int bj = (lane < 3) ? 0 : (lane < 5 ? 1 : 2);
-              S[cidx(3 + bi, 3 + bj)] = pick6(soo, lane);
+            if (lane == 0) {
+              S[cidx(3, 3)] = soo[0]; S[cidx(4, 3)] = soo[1]; S[cidx(5, 3)] = soo[2];
+              S[cidx(4, 4)] = soo[3]; S[cidx(5, 4)] = soo[4]; S[cidx(5, 5)] = soo[5];
             }
             // mu (+)= delta on the vector components: tangent x -> stored x (x < 3) or x + 1 (x >= 6)
             if (x0 < 3) mu[x0] += dl[0];

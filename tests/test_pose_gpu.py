@@ -513,6 +513,59 @@ def test_pipelined_host_step_equals_direct_calls(pkg, syn, scen):
     a.close(); b.close()
 
 
+def test_two_handles_on_two_streams_are_independent(pkg, syn, scen):
+    """Distinct handles are independent (include/uwvkf.h): two batches stepping concurrently on two non-blocking streams give
+    the results of running them one after the other."""
+    import torch
+    B = 20000
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    filt_a, filt_b = np.arange(B), np.arange(B, 2 * B)
+    ref = []
+    for filt in (filt_a, filt_b):
+        u, *_ = make_batch(pkg, syn, scen, B, first_filter=int(filt[0]))
+        for s in range(1, 4):
+            inp = syn.pose_inputs(filt, s)
+            u.predict_update(DT, inp["gyro"], pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+            u.integrate_measurement(pkg.POSE_ACCELERATION, inp["acc"], syn.R_ACC)
+        ref.append(u.get_state(with_cov=False)); u.close()
+    mu_a, cov_a = syn.pose_initial_batch(filt_a, scen["cfg"])
+    mu_b, cov_b = syn.pose_initial_batch(filt_b, scen["cfg"])
+    a = pkg.PoseUKFBatch(B, scen["par"], stream=sa.cuda_stream); a.set_process_noise(scen["Q"]); a.set_state(mu_a, cov_a)
+    b = pkg.PoseUKFBatch(B, scen["par"], stream=sb.cuda_stream); b.set_process_noise(scen["Q"]); b.set_state(mu_b, cov_b)
+    dev = {}
+    for s in range(1, 4):
+        for name, filt in (("a", filt_a), ("b", filt_b)):
+            inp = syn.pose_inputs(filt, s)
+            dev[name, s] = {k: torch.from_numpy(np.ascontiguousarray(inp[k])).cuda() for k in ("gyro", "dvl", "acc")}
+    torch.cuda.synchronize()
+    for s in range(1, 4):                                   # interleaved submission, nothing synchronises in between
+        for u, name in ((a, "a"), (b, "b")):
+            d_ = dev[name, s]
+            u.predict_update(DT, d_["gyro"].data_ptr(), pkg.POSE_VELOCITY, d_["dvl"].data_ptr(), syn.R_DVL, memspace=pkg.DEVICE)
+            u.integrate_measurement(pkg.POSE_ACCELERATION, d_["acc"].data_ptr(), syn.R_ACC, memspace=pkg.DEVICE)
+    a.synchronize(); b.synchronize()
+    assert np.array_equal(a.get_state(with_cov=False), ref[0]) and np.array_equal(b.get_state(with_cov=False), ref[1])
+    assert not a.get_status().any() and not b.get_status().any()
+    a.close(); b.close()
+
+
+def test_host_step_argument_checks(pkg, syn, scen):
+    B = 64
+    ukf, filt, mu, cov, off = make_batch(pkg, syn, scen, B)
+    inp = syn.pose_inputs(filt, 1)
+    g, z = np.ascontiguousarray(inp["gyro"]), np.ascontiguousarray(inp["dvl"])
+    ukf.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL)                 # no read-back requested
+    ukf.synchronize()
+    other, *_ = make_batch(pkg, syn, scen, B)
+    other.predict_update(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL)
+    assert all(np.array_equal(x, y) for x, y in zip(ukf.get_state(), other.get_state()))
+    with pytest.raises(pkg.UwvkfError):                                   # six-dimensional kinds are not part of the pipelined step
+        ukf.step_host(DT, g, pkg.POSE_BODY_EFFORTS, np.zeros((B, 6)), np.eye(6))
+    with pytest.raises(pkg.UwvkfError):
+        ukf.step_host(float("nan"), g, pkg.POSE_VELOCITY, z, syn.R_DVL)
+    ukf.close(); other.close()
+
+
 def test_cuda_graph_replay_of_a_schedule(pkg, syn, scen):
     """A K-step schedule (rotation rate + fused predict/DVL + acceleration per step, inputs resident in HBM) captured once into a
     CUDA graph and replayed == the same calls issued one by one."""
