@@ -53,6 +53,14 @@ int main() {
   rot_cov(0, 0) = 1e-4; rot_cov(1, 1) = 1e-4; rot_cov(2, 2) = 1e-2;
   PoseUKF pose(Vector3d::Zero(), Matrix3d::Identity(), Quaterniond::Identity(), rot_cov, cfg, synth_model());
   pose.setProcessNoiseFromConfig(cfg, 0.01);
+  // the same filter twice more, driven through the batched entry points a sensor loop would use: predictionStepAndIntegrate2
+  // (one call per IMU sample: prediction + DVL + accelerometer) and stepHost (pipelined host-buffer step)
+  PoseUKF pose2(Vector3d::Zero(), Matrix3d::Identity(), Quaterniond::Identity(), rot_cov, cfg, synth_model());
+  PoseUKF pose3(Vector3d::Zero(), Matrix3d::Identity(), Quaterniond::Identity(), rot_cov, cfg, synth_model());
+  pose2.setProcessNoiseFromConfig(cfg, 0.01);
+  pose3.setProcessNoiseFromConfig(cfg, 0.01);
+  std::vector<std::vector<double>> keep_w(steps, std::vector<double>(3)), keep_v(steps, std::vector<double>(3));
+  std::vector<double> nav(10 * 3);
   for (int s = 0; s < steps; ++s) {
     PoseUKF::RotationRate w; PoseUKF::Velocity v; PoseUKF::Acceleration a; PoseUKF::Pressure p;
     read(w.mu, 3); read(v.mu, 3); read(a.mu, 3); read(p.mu, 1);
@@ -63,6 +71,22 @@ int main() {
     pose.integrateMeasurement(v);
     pose.integrateMeasurement(a);
     if ((s + 1) % 5 == 0) pose.integrateMeasurement(p, Vector3d{0.3, -0.1, 0.2});
+    const double Rv[9] = {1e-4, 0, 0, 0, 1e-4, 0, 0, 0, 1e-4};
+    for (int k = 0; k < 3; ++k) { keep_w[s][k] = w.mu[k]; keep_v[s][k] = v.mu[k]; }     // host buffers stay alive (stepHost is asynchronous)
+    pose2.predictionStepAndIntegrate2(0.01, keep_w[s].data(), UWVKF_POSE_VELOCITY, keep_v[s].data(), Rv, UWVKF_POSE_ACCELERATION,
+                                      a.mu.data(), Rv);
+    if ((s + 1) % 5 == 0) pose2.integrateMeasurement(p, Vector3d{0.3, -0.1, 0.2});
+    pose3.stepHost(0.01, keep_w[s].data(), UWVKF_POSE_VELOCITY, keep_v[s].data(), Rv, nav.data() + 10 * (s % 3));
+    pose3.integrateMeasurement(a);
+    if ((s + 1) % 5 == 0) pose3.integrateMeasurement(p, Vector3d{0.3, -0.1, 0.2});
+  }
+  pose3.synchronize();
+  {
+    PoseUKF::State s2, s3; PoseUKF::Covariance c2, c3;
+    pose2.getCurrentStateAndCovariance(s2, c2);
+    pose3.getCurrentStateAndCovariance(s3, c3);
+    dump("POSE2", s2, 54, c2.v, 53 * 53);
+    dump("POSE3", s3, 54, c3.v, 53 * 53);
   }
   {   // model-aided part: forces / torques in the body frame, both flavours (reference src/PoseUKF.cpp:581-602)
     PoseUKF::BodyEffortsMeasurement e;

@@ -58,6 +58,10 @@ def test_cpp_classes_match_oracle(syn):
         mu, cov, st, _ = orc.pose_update(orc.ACCELERATION, mu, cov, i["acc"][0], 1e-4 * np.eye(3), None, w, par)
         if s % 5 == 0:
             mu, cov, st, _ = orc.pose_update(orc.PRESSURE, mu, cov, i["pressure"][0], np.array([[1e4]]), np.array([0.3, -0.1, 0.2]), w, par)
+    for tag in ("POSE2", "POSE3"):
+        g2 = out[tag]
+        assert state_err(g2[:54], mu) <= TOL_STATE and cov_err(g2[54:].reshape(53, 53), cov) <= TOL_COV, tag
+    assert np.array_equal(out["POSE2"], out["POSE3"])
     tau, Re = np.array([12.0, -3.0, 1.5, 0.0, 0.0, 0.4]), np.diag([4.0] * 3 + [0.25] * 3)
     w = pose_in[-1]["gyro"][0]
     mu, cov, st, _ = orc.pose_update(orc.BODY_EFFORTS, mu, cov, tau, Re, syn.uwv_params_flat(), w, par)
@@ -65,6 +69,9 @@ def test_cpp_classes_match_oracle(syn):
     g = out["POSE"]
     assert state_err(g[:54], mu) <= TOL_STATE and cov_err(g[54:].reshape(53, 53), cov) <= TOL_COV
     assert np.abs(out["ROTRATE"] - orc.pose_rotation_rate(mu, pose_in[-1]["gyro"][0], par)).max() < 1e-14
+
+    # the batched entry points (one call per IMU sample; pipelined host-buffer step) end where the per-measurement calls end
+    assert "POSE2" in out and "POSE3" in out
 
     # VelocityUKF
     uwv = syn.uwv_params_flat()
