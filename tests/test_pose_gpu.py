@@ -468,6 +468,10 @@ def test_sample_stream_replays_like_direct_calls(pkg, syn, scen):
     assert stream.pending == 0 and abs(stream.time - (t0 + STEPS * DT)) < 1e-9
     with pytest.raises(pkg.UwvkfError):      # time must not run backwards
         stream.push(t0, pkg.POSE_VELOCITY, inp["dvl"], syn.R_DVL)
+    znan = inp["dvl"].copy(); znan[-1, 2] = np.nan
+    with pytest.raises(pkg.UwvkfError) as ei:   # a NaN sample is refused before the slot is touched: the ring is unchanged
+        stream.push(t0 + (STEPS + 1) * DT, pkg.POSE_VELOCITY, znan, syn.R_DVL)
+    assert ei.value.code == -4 and stream.pending == 0
     ma, ca = a.get_state()
     mb, cb = b.get_state()
     # predict dt: the stream derives it from timestamps (t0 + s DT differences), the direct path passes DT itself
