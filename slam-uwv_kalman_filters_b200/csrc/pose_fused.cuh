@@ -180,7 +180,8 @@ struct FusedCfg {
   // alternating per filter (the next filter's inputs arrive while the current filter's update still reads its own)
   static constexpr int INW = (KIND2 == M_NONE) ? 8 : 12;
   static constexpr int O_IN = O_LT + NT * KE;
-  static constexpr int TOTAL = O_IN + 2 * INW;
+  static constexpr int O_MB = O_IN + 2 * INW;      // mbarrier of the bulk (TMA) prefix fetch (8 bytes; 16 reserved)
+  static constexpr int TOTAL = O_MB + 2;
   // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
@@ -214,6 +215,9 @@ struct FusedCfg {
 #endif
 #ifndef UWVKF_LANE_PINNED         // 1: the lane index cannot be re-materialised from SR_TID inside the filter loop
 #define UWVKF_LANE_PINNED 0
+#endif
+#ifndef UWVKF_TMA_PREFIX          // 1: the [mu | panel] prefix arrives by ONE bulk copy (TMA engine, cp.async.bulk + mbarrier) per filter
+#define UWVKF_TMA_PREFIX 1
 #endif
 #ifndef UWVKF_ILV_EARLY           // 1: request the first batches before the panel downdate instead of after it
 #define UWVKF_ILV_EARLY 0
@@ -769,13 +773,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   // are waited for at the top of the next iteration.
   constexpr int NV = (56 + C::PANEL_E) / 2;
   const unsigned w_saddr = (unsigned)__cvta_generic_to_shared(w);
+#if UWVKF_TMA_PREFIX
+  // The 6-7 KB prefix is one contiguous, 16-byte aligned range in global and in shared memory: ONE bulk copy of the TMA engine
+  // (cp.async.bulk, SASS UBLKCP) issued by lane 0 brings it in and signals the warp's mbarrier with the byte count, instead of
+  // a dozen 16-byte cp.async per lane.  The warp waits on the barrier's phase at the top of the next filter.
+  const unsigned mb_saddr = w_saddr + 8u * C::O_MB;
+  unsigned mb_phase = 0;
+  if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb_saddr) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+#endif
   auto fetch_prefix = [&](long long ff, unsigned pr) {
     const char *src = reinterpret_cast<const char *>(a.state + ff * BLK);
     const unsigned dsta = w_saddr + 8u * C::O_A;
+#if UWVKF_TMA_PREFIX
+    // the buffer was last touched through the generic proxy (write-back loads, panel stores): order those before the engine's writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb_saddr), "r"((unsigned)(NV * 16)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsta), "l"(src),
+                   "r"((unsigned)(NV * 16)), "r"(mb_saddr) : "memory");
+    }
+#else
 #pragma unroll 4
     for (int k = lane; k < NV; k += 32)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta + 16u * k), "l"(src + 16 * k) : "memory");
-    // the filter's small inputs ride in the same group, so no global-memory round trip is left inside the iteration
+#endif
+    // the filter's small inputs ride in a cp.async group, so no global-memory round trip is left inside the iteration
     const unsigned ina = w_saddr + 8u * (C::O_IN + (unsigned)C::INW * pr);
     if (HAS_PREDICT && lane < 3)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(a.rot_rate + ff * 3 + lane) : "memory");
@@ -803,6 +828,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #endif
     PH_DECL
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if UWVKF_TMA_PREFIX
+    {   // the bulk copy of this filter's prefix has completed its transaction bytes when the barrier's phase flips
+      unsigned done;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb_saddr), "r"(mb_phase) : "memory");
+      } while (!done);
+      mb_phase ^= 1u;
+    }
+#endif
     __syncwarp();
     // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
     // prefix of the warp's next filter into L2 now; also fetch the small per-filter inputs early
