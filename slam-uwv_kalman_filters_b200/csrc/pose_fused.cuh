@@ -23,6 +23,18 @@ namespace pose {
 
 constexpr int M_NONE = -1;
 
+#ifndef UWVKF_ILV                 // 1: trailing pass of the predict+update kernels interleaved with apply_delta (TrailStream)
+#define UWVKF_ILV 1
+#endif
+#ifndef UWVKF_ILV_UPDATE_ONLY     // 1: the update-only kernels interleave their trailing pass as well
+#define UWVKF_ILV_UPDATE_ONLY 1
+#endif
+#ifndef UWVKF_TMA_PREFIX          // 1: the [mu | panel] prefix arrives by ONE bulk copy (TMA engine, cp.async.bulk + mbarrier) per filter
+#define UWVKF_TMA_PREFIX 1
+#endif
+#ifndef UWVKF_TMA_TRAIL           // 1: the interleaved trailing pass reads from a staging buffer filled by one bulk copy per filter
+#define UWVKF_TMA_TRAIL 1
+#endif
 #ifndef UWVKF_SHRINK              // 1: predict kernels shrink the panel to 9 columns after the predict's factorisation (FusedCfg::KT): parity green, 2 % slower, off
 #define UWVKF_SHRINK 0
 #endif
@@ -180,8 +192,16 @@ struct FusedCfg {
   // alternating per filter (the next filter's inputs arrive while the current filter's update still reads its own)
   static constexpr int INW = (KIND2 == M_NONE) ? 8 : 12;
   static constexpr int O_IN = O_LT + NT * KE;
-  static constexpr int O_MB = O_IN + 2 * INW;      // mbarrier of the bulk (TMA) prefix fetch (8 bytes; 16 reserved)
-  static constexpr int TOTAL = O_MB + 2;
+  static constexpr int O_MB = O_IN + 2 * INW;      // mbarriers of the bulk (TMA) copies: [0] prefix fetch, [1] trailing triangle
+  // The interleaved trailing pass reads the old trailing triangle from a shared-memory STAGING buffer that ONE bulk copy fills at
+  // the top of the filter's iteration (UWVKF_TMA_TRAIL): no loads in flight in registers across the phases of apply_delta, no
+  // L2 prefetch.  The copy starts at the even entry at or below the panel's end (16-byte alignment) and runs to the block's end.
+  static constexpr bool TRS = UWVKF_TMA_TRAIL && UWVKF_TMA_PREFIX && UWVKF_ILV && KIND != M_NONE && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY) &&
+                              !(UWVKF_SHRINK);
+  static constexpr int TR_START = PANEL & ~1;                       // first staged entry (packed index)
+  static constexpr int TR_LEN = TRS ? (BLK - OFF_S) - TR_START : 0;  // doubles staged (through the pad at the end of the block)
+  static constexpr int O_TR = O_MB + 2;
+  static constexpr int TOTAL = O_TR + TR_LEN;
   // per-CTA shared region (doubles): dt^2 Q packed (predict only), parameter tables
   static constexpr int C_Q = 0;
   static constexpr int C_FTAB = HAS_PREDICT ? 1432 : 0;       // affine factor per tangent index
@@ -198,9 +218,6 @@ struct FusedCfg {
 #ifndef UWVKF_TRAIL_PREFETCH_L1   // 1: pull the trailing triangle into L1 instead of L2 at the top of a filter (measured: no gain)
 #define UWVKF_TRAIL_PREFETCH_L1 0
 #endif
-#ifndef UWVKF_ILV                 // 1: trailing pass of the predict+update kernels interleaved with apply_delta (TrailStream)
-#define UWVKF_ILV 1
-#endif
 #ifndef UWVKF_OPAQUE_LANE         // 1: lane index opaque per filter (no loop-invariant hoisting of lane-derived values)
 #define UWVKF_OPAQUE_LANE 0
 #endif
@@ -216,14 +233,8 @@ struct FusedCfg {
 #ifndef UWVKF_LANE_PINNED         // 1: the lane index cannot be re-materialised from SR_TID inside the filter loop
 #define UWVKF_LANE_PINNED 0
 #endif
-#ifndef UWVKF_TMA_PREFIX          // 1: the [mu | panel] prefix arrives by ONE bulk copy (TMA engine, cp.async.bulk + mbarrier) per filter
-#define UWVKF_TMA_PREFIX 1
-#endif
 #ifndef UWVKF_ILV_EARLY           // 1: request the first batches before the panel downdate instead of after it
 #define UWVKF_ILV_EARLY 0
-#endif
-#ifndef UWVKF_ILV_UPDATE_ONLY     // 1: the update-only kernels interleave their trailing pass as well
-#define UWVKF_ILV_UPDATE_ONLY 1
 #endif
 #ifndef UWVKF_ILV_PREDICT         // 1: the predict-only kernel interleaves its trailing pass with the predict's own phases: parity green, 4 % slower (spills), off
 #define UWVKF_ILV_PREDICT 0
@@ -607,9 +618,12 @@ __device__ __noinline__ void trailing_pass_cold(double *gS, const double *Qs, co
 // L2 latency (the triangle was prefetched at the top of the filter) hides behind that phase, and the FMAs / stores of the
 // previous batch fill the issue slots the phase leaves empty.  Nothing is stored before the factorisation of apply_delta has
 // succeeded (a failure rolls the update back: the batches in flight are dropped and the classic pass applies the process map only).
-template <bool AP, int KP, int M, int UB, int DEPTH, int M2 = 0>
+// STAGED: the old values come from a shared-memory copy of the triangle (tr[e] = entry e of the packed array; one TMA bulk copy
+// per filter) and are read where they are consumed: load() does nothing and no value is in flight across a phase.
+template <bool AP, int KP, int M, int UB, int DEPTH, int M2 = 0, bool STAGED = false>
 struct TrailStream {
   static constexpr int KCW = M2 > 0 ? 8 : 4;
+  const double *tr = nullptr;
   static constexpr int NB = (N - KP + UB - 1) / UB;
   static constexpr int NS = KP <= 20 ? 21 - KP : 0;
   double v[DEPTH][UB];
@@ -637,7 +651,7 @@ struct TrailStream {
     return sv;
   }
   template <int I> __device__ __forceinline__ void load(const double *gS, int lane) {
-    if constexpr (I < NB) {
+    if constexpr (I < NB && !STAGED) {
       const int rP = lane <= 20 ? lane + 32 : lane;
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
@@ -652,8 +666,10 @@ struct TrailStream {
     }
   }
   __device__ __forceinline__ void load_secondary(const double *gS, int lane) {
+    if constexpr (!STAGED) {
 #pragma unroll
-    for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lane <= 20 && lane >= KP + u) ? lane : KP + u));
+      for (int u = 0; u < NS; ++u) vS[u] = ldcs_v(gS + coloff(KP + u) + ((lane <= 20 && lane >= KP + u) ? lane : KP + u));
+    }
   }
   template <int I> __device__ __forceinline__ void finish(bool on, double *gS, const double *Qs, const double *KC, const double (&f)[2],
                                                           const double (&ks)[2][3], double q2add, int lane,
@@ -678,7 +694,8 @@ struct TrailStream {
 #elif UWVKF_EXP_NOSTORE  // experiment: no stores (WRONG results; timing only)
           if (entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2) == 1.2345e-300) stcs_if(on && rP >= b, gS + coloff(b) + rowP, 0.0);
 #else
-          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, v[I % DEPTH][u], fP, kP0, kP1, kP2, jP0, jP1, jP2));
+          const double old = STAGED ? tr[coloff(b) + rowP] : v[I % DEPTH][u];
+          stcs_if(on && rP >= b, gS + coloff(b) + rowP, entry(Qs, KC, q2add, b, rowP, old, fP, kP0, kP1, kP2, jP0, jP1, jP2));
 #endif
         }
       }
@@ -692,8 +709,9 @@ struct TrailStream {
       const int b = KP + u;
       const bool actS = lane <= 20 && lane >= b;
       const int rowS = actS ? lane : b;
+      const double old = STAGED ? tr[coloff(b) + rowS] : vS[u];
       stcs_if(on && actS, gS + coloff(b) + rowS,
-              entry(Qs, KC, q2add, b, rowS, vS[u], f[0], ks[0][0], ks[0][1], ks[0][2], ks2[0][0], ks2[0][1], ks2[0][2]));
+              entry(Qs, KC, q2add, b, rowS, old, f[0], ks[0][0], ks[0][1], ks[0][2], ks2[0][0], ks2[0][1], ks2[0][2]));
     }
   }
 };
@@ -778,8 +796,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
   // (cp.async.bulk, SASS UBLKCP) issued by lane 0 brings it in and signals the warp's mbarrier with the byte count, instead of
   // a dozen 16-byte cp.async per lane.  The warp waits on the barrier's phase at the top of the next filter.
   const unsigned mb_saddr = w_saddr + 8u * C::O_MB;
-  unsigned mb_phase = 0;
+  unsigned mb_phase = 0, tr_phase = 0;
+  (void)tr_phase;
   if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb_saddr) : "memory");
+  if (C::TRS && lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb_saddr + 8u) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
 #endif
@@ -841,9 +861,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     __syncwarp();
     // hide HBM latency behind the panel work: pull this filter's trailing triangle (read at the very end) and the
     // prefix of the warp's next filter into L2 now; also fetch the small per-filter inputs early
+    bool tr_waited = !C::TRS;
+    auto tr_wait = [&]() {   // the staged triangle has landed (once per filter, on whichever path gets there first)
+#if UWVKF_TMA_PREFIX
+      if constexpr (C::TRS) {
+        if (!tr_waited) {
+          unsigned done;
+          do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mb_saddr + 8u), "r"(tr_phase) : "memory");
+          } while (!done);
+          tr_phase ^= 1u;
+          tr_waited = true;
+        }
+      }
+#endif
+    };
     {
       const char *tr = reinterpret_cast<const char *>(blk + OFF_S + C::PANEL);   // (columns KT..KP-1 arrive with the prefix)
       constexpr int TB = (NP - C::PANEL) * 8;
+#if UWVKF_TMA_PREFIX
+      if constexpr (C::TRS) {
+        // this filter's trailing triangle -> staging buffer, one bulk copy; it is consumed by the interleaved pass, a whole
+        // predict (or, in the update-only kernels, a factorisation and a set of sigma points) later
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          constexpr unsigned bytes = (unsigned)C::TR_LEN * 8u;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb_saddr + 8u), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w_saddr + 8u * C::O_TR),
+                       "l"(reinterpret_cast<const char *>(blk + OFF_S + C::TR_START)), "r"(bytes), "r"(mb_saddr + 8u) : "memory");
+        }
+      } else
+#endif
 #if UWVKF_TRAIL_PREFETCH_L1
       for (int o = lane * 128; o < TB; o += 32 * 128) prefetch_l1(tr + o);
 #else
@@ -1280,7 +1330,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           // the factorisation of apply_delta
           constexpr bool ILV = UWVKF_ILV && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY) && !DEFER;
           constexpr int M1_ = SECOND ? C::MF::M : M, M2_ = SECOND ? M : 0;   // the pass of a second update carries both downdates
-          TrailStream<HAS_PREDICT != 0, KT, M1_, UWVKF_ILV_UB, UWVKF_ILV_DEPTH, M2_> ts;
+          TrailStream<HAS_PREDICT != 0, KT, M1_, UWVKF_ILV_UB, UWVKF_ILV_DEPTH, M2_, C::TRS> ts;
+          if constexpr (C::TRS) { tr_wait(); ts.tr = w + C::O_TR - C::TR_START; }
           // Filters whose prediction was refused (rare) still run the batches -- no branch around loads whose values are consumed
           // several phases later -- but with every store predicated off; the classic pass then handles them
           const bool ilv = ILV && (HAS_PREDICT ? predicted : true);
@@ -1501,6 +1552,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       if (fn < a.B) fetch_prefix(fn, par ^ 1u);
     }
     par ^= 1u;
+    tr_wait();   // (filters that never reached the interleaved pass: the barrier's phase still has to be consumed)
     if (st && lane == 0) a.status[f] |= st;
     __syncwarp();
     PH(29);
