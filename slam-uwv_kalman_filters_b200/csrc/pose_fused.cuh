@@ -196,8 +196,7 @@ struct FusedCfg {
   // The interleaved trailing pass reads the old trailing triangle from a shared-memory STAGING buffer that ONE bulk copy fills at
   // the top of the filter's iteration (UWVKF_TMA_TRAIL): no loads in flight in registers across the phases of apply_delta, no
   // L2 prefetch.  The copy starts at the even entry at or below the panel's end (16-byte alignment) and runs to the block's end.
-  static constexpr bool TRS = UWVKF_TMA_TRAIL && UWVKF_TMA_PREFIX && UWVKF_ILV && KIND != M_NONE && (HAS_PREDICT || UWVKF_ILV_UPDATE_ONLY) &&
-                              !(UWVKF_SHRINK);
+  static constexpr bool TRS = UWVKF_TMA_TRAIL && UWVKF_TMA_PREFIX && !(UWVKF_SHRINK);
   static constexpr int TR_START = PANEL & ~1;                       // first staged entry (packed index)
   static constexpr int TR_LEN = TRS ? (BLK - OFF_S) - TR_START : 0;  // doubles staged (through the pad at the end of the block)
   static constexpr int O_TR = O_MB + 2;
@@ -715,6 +714,23 @@ struct TrailStream {
     }
   }
 };
+
+// The same pass with the old values in the shared-memory staging copy of the triangle (tr[e] = entry e of the packed array, one
+// TMA bulk copy per filter): nothing to pipeline, every column is a shared-memory read, the arithmetic and a predicated store.
+template <bool AP, bool AK, int KP, int M, int M2 = 0>
+__device__ __forceinline__ void trailing_pass_staged(double *__restrict__ gS, const double *tr, const double *Qs, const double *KC,
+                                                     const double (&f)[2], const double (&ks)[2][3], double q2add, int lane,
+                                                     const double (&ks2)[2][3] = kNoKs) {
+  using TS = TrailStream<AP, KP, AK ? M : 0, 8, 1, M2, true>;
+  TS ts;
+  ts.tr = tr;
+  ts.finish_secondary(true, gS, Qs, KC, f, ks, q2add, lane, ks2);
+  auto step = [&](auto i_) { ts.template finish<decltype(i_)::value>(true, gS, Qs, KC, f, ks, q2add, lane, ks2); };
+  step(std::integral_constant<int, 0>{}); step(std::integral_constant<int, 1>{}); step(std::integral_constant<int, 2>{});
+  step(std::integral_constant<int, 3>{}); step(std::integral_constant<int, 4>{}); step(std::integral_constant<int, 5>{});
+  step(std::integral_constant<int, 6>{}); step(std::integral_constant<int, 7>{});
+  static_assert(TS::NB <= 8, "more batches");
+}
 
 // -1/tau of stored component s (0 when the process model leaves it alone), reference src/PoseUKF.cpp:37-78
 __device__ inline double markov_rate(int s, const Params &P) {
@@ -1526,6 +1542,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
 #endif
       if (trailing_done || UWVKF_EXP_SKIPTRAIL) {
         // the interleaved pass (TrailStream) has already rewritten the trailing triangle
+      } else if constexpr (C::TRS && KIND == M_NONE) {
+        // predict-only kernel: this IS the hot path -- old values from the staging copy (one bulk copy per filter), nothing to
+        // pipeline.  (The kernels with an update come here for refused filters only and keep the pipelined pass from HBM: giving
+        // them the staged form as well costs the fused predict + DVL kernel 5 % -- register allocation again.)
+        tr_wait();
+        trailing_pass_staged<true, false, KT, MM_>(gS, w + C::O_TR - C::TR_START, Qs, KC, frow, ksr, q2add, tlane);
       } else if constexpr (KIND2 != M_NONE) {   // both downdates in one pass; refused updates carry zero factors
         if (HAS_PREDICT && predicted) trailing_pass<true, true, KT, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
         else trailing_pass<false, true, KT, MM_, TUB, TDEPTH, C::MF2::M>(gS, Qs, KC, frow, ksr, q2add, tlane, ksr2);
