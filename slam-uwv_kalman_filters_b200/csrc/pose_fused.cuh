@@ -196,8 +196,8 @@ struct FusedCfg {
   // The interleaved trailing pass reads the old trailing triangle from a shared-memory STAGING buffer that ONE bulk copy fills at
   // the top of the filter's iteration (UWVKF_TMA_TRAIL): no loads in flight in registers across the phases of apply_delta, no
   // L2 prefetch.  The copy starts at the even entry at or below the panel's end (16-byte alignment) and runs to the block's end.
-  static constexpr bool TRS = UWVKF_TMA_TRAIL && UWVKF_TMA_PREFIX && !(UWVKF_SHRINK);
-  static constexpr int TR_START = PANEL & ~1;                       // first staged entry (packed index)
+  static constexpr bool TRS = UWVKF_TMA_TRAIL && UWVKF_TMA_PREFIX;
+  static constexpr int TR_START = PANEL_T & ~1;                     // first staged entry (packed index): where the trailing pass starts
   static constexpr int TR_LEN = TRS ? (BLK - OFF_S) - TR_START : 0;  // doubles staged (through the pad at the end of the block)
   static constexpr int O_TR = O_MB + 2;
   static constexpr int TOTAL = O_TR + TR_LEN;
