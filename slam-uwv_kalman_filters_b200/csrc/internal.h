@@ -44,6 +44,7 @@ struct uwvkf_filter_s {
   double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr, *d_uwv = nullptr;
   uwvkf::pose::Params pp{};
   bool have_params = false, have_Q = false;
+  double *nav_fused = nullptr;   // set around the fused launch of uwvkf_pose_step_host: the kernel writes the navigation solution itself
   // uwvkf_pose_step_host: two input slots / two navigation buffers, upload and download streams, events per slot
   struct HostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -67,6 +67,8 @@ struct Launch {
   uint32_t *status;        // [B]
   const double *Q;         // packed lower, column-major, NP doubles
   const double *uwv;       // NUWV doubles (motion-model parameters of the constructor, src/PoseUKF.cpp:353-354) or nullptr
+  double *nav;             // [B][10] or nullptr: the fused kernel also writes p(3) q(4) v(3) of every filter after the step (the
+                           // navigation read-back of uwvkf_pose_step_host without a second kernel and a second pass over mu)
   long long B;
   int nops;
   Op ops[3];

@@ -451,11 +451,16 @@ int launch_fused_kind(uwvkf_handle h, const pose::Launch &L, int kind) {
   }
   return fail(UWVKF_ERR_INVALID_ARGUMENT, "measurement kind not handled by the fused kernel");
 }
+bool engine_v1() {
+  static const bool v1 = [] { const char *e = std::getenv("UWVKF_ENGINE"); return e && std::string(e) == "v1"; }();
+  return v1;
+}
 int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   if (!h->have_params) return fail(UWVKF_ERR_NOT_INITIALIZED, "uwvkf_pose_set_params was not called");
   pose::Launch L{};
   L.state = h->d_state; L.offsets = h->d_offsets; L.rot_rate = h->d_rot; L.status = h->d_status; L.Q = h->d_Q;
   L.uwv = h->d_uwv;
+  L.nav = h->nav_fused;
   L.B = h->B; L.nops = nops;
   bool slow = false, dense_only = false, full_efforts = false;
   for (int o = 0; o < nops; ++o) {
@@ -471,7 +476,7 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   // engine selection: "panel + stream" kernel for predict / update / predict+update (pressure and ADCP through their
   // affine tail); the resident kernel (dense prefix 53 for pressure / ADCP) for op sequences the fused kernel has no
   // instantiation for and, with UWVKF_ENGINE=v1, for everything (cross-checks)
-  static const bool force_v1 = [] { const char *e = std::getenv("UWVKF_ENGINE"); return e && std::string(e) == "v1"; }();
+  const bool force_v1 = engine_v1();
   if (!force_v1 && !dense_only) {
     if (nops == 1 && ops[0].type == 0) return launch_fused<1, pose::M_NONE>(h, L);
     if (nops == 1 && ops[0].type == 1) return launch_fused_kind<0>(h, L, ops[0].kind);
@@ -1186,9 +1191,13 @@ int uwvkf_pose_step_host(uwvkf_handle h, double dt, const double *w_host, int me
   CK(cudaEventRecord(p->ev_in[slot], p->s_in));
   // fused step on the handle's stream (the navigation buffer of this slot was read back two calls ago: waited for above)
   CK(cudaStreamWaitEvent(h->stream, p->ev_in[slot], 0));
+  // the fused kernel stores the navigation solution of every filter itself (Launch::nav): no second kernel, no second pass over mu
+  const bool nav_in_kernel = nav_out_host && !engine_v1();
+  h->nav_fused = nav_in_kernel ? p->d_nav[slot] : nullptr;
   int rc = uwvkf_pose_predict_update(h, dt, p->d_w[slot], meas_kind, p->d_z[slot], R, 0, aux, nullptr, UWVKF_DEVICE);
+  h->nav_fused = nullptr;
   if (rc) return rc;
-  if (nav_out_host) {
+  if (nav_out_host && !nav_in_kernel) {
     rc = uwvkf_pose_get_navigation(h, p->d_nav[slot], 0, h->B, UWVKF_DEVICE);
     if (rc) return rc;
   }

@@ -510,10 +510,12 @@ def test_pipelined_host_step_equals_direct_calls(pkg, syn, scen):
     # NaN samples are refused per filter on the device (the pipelined call does not scan host memory)
     g, z = ring_in[0]
     z[5, 1] = np.nan
-    a.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL)
+    a.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL, nav_out=ring_nav[0])
     a.synchronize()
     st = a.get_status()
     assert st[5] & pkg.ST_NAN_MEASUREMENT and np.count_nonzero(st) == 1
+    # the navigation solution comes out of the fused kernel itself: also for the filter whose update was refused
+    assert np.array_equal(ring_nav[0], a.get_navigation())
     a.close(); b.close()
 
 
