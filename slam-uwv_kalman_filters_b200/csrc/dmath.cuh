@@ -307,6 +307,129 @@ __device__ __forceinline__ void tmerc_nav_to_sincos_lat(const TMercConst &tm, do
   cos_lat = cch * ce - sch * se;
 }
 
+// The `near` path of tmerc_nav_to_sincos_lat as STRAIGHT-LINE code (same operations in the same order: bit-identical results
+// where it applies); returns false when an argument leaves the range of the small-argument polynomials, and the caller then
+// calls the generic routine.  Without branches the whole evaluation is one basic block, which lets the instruction scheduler
+// interleave its long dependent chain with whatever the caller has around it (the panel Cholesky of the predict).
+__device__ __forceinline__ bool tmerc_nav_to_sincos_lat_near(const TMercConst &tm, double x, double y, double &sin_lat, double &cos_lat) {
+  const double dx = x * tm.Ainv;
+  double eta = -y * tm.Ainv;
+  bool ok = fabs(dx) <= 0.0625 && fabs(eta) <= 0.0625;
+  double s1, c1, sh2, ch2;
+  {
+    double sd_, cd_;
+    sincos_small(dx, sd_, cd_);
+    s1 = fma(tm.sin_xi0, cd_, tm.cos_xi0 * sd_);
+    c1 = fma(tm.cos_xi0, cd_, -(tm.sin_xi0 * sd_));
+    sinhcosh_small(2 * eta, sh2, ch2);
+  }
+  double s2 = 2 * s1 * c1, c2 = fma(-2 * s1, s1, 1.0);
+  double sj = s2, cj = c2, shj = sh2, chj = ch2;
+  double dxi = 0, deta = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    dxi = fma(tm.beta[j] * sj, chj, dxi);
+    deta = fma(tm.beta[j] * cj, shj, deta);
+    double sn = sj * c2 + cj * s2, cn = cj * c2 - sj * s2;
+    double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
+    sj = sn; cj = cn; shj = shn; chj = chn;
+  }
+  ok = ok && fabs(dxi) <= 0.0625;
+  double sd, cd, chp, shp;
+  sincos_small(dxi, sd, cd);
+  sinhcosh_small(eta - deta, shp, chp);
+  double sxp = s1 * cd - c1 * sd;
+  double sch = sxp * fast_rcp(chp);
+  double cch = sqrt(fma(-sch, sch, 1.0));
+  double sc = 2 * sch * cch, cc = fma(-2 * sch, sch, 1.0);
+  double sk = sc, ck = cc, eps = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    eps = fma(tm.delta[j], sk, eps);
+    double sn = sk * cc + ck * sc, cn = ck * cc - sk * sc;
+    sk = sn; ck = cn;
+  }
+  ok = ok && fabs(eps) <= 0.0625;
+  double se, ce;
+  sincos_small(eps, se, ce);
+  sin_lat = sch * ce + cch * se;
+  cos_lat = cch * ce - sch * se;
+  return ok;
+}
+
+// The same evaluation cut into STAGES of a few dependent operations each.  The predict calls one stage per column of its
+// panel Cholesky (from column 1 on): both are single long dependent chains, and side by side in the instruction stream they
+// fill each other's latency (ptxas interleaves neighbouring independent chains, it does not pull a 700-cycle chain apart).
+struct TMercStages {
+  double eta, s1, c1, s2, c2, sh2, ch2, sj, cj, shj, chj, dxi, deta, sd, cd, chp, sch, cch, sc, cc, sk, ck, eps;
+  bool ok;
+  double sin_lat, cos_lat;
+  template <int J>
+  __device__ __forceinline__ void series1(const TMercConst &tm) {
+    dxi = fma(tm.beta[J] * sj, chj, dxi);
+    deta = fma(tm.beta[J] * cj, shj, deta);
+    const double sn = sj * c2 + cj * s2, cn = cj * c2 - sj * s2;
+    const double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
+    sj = sn; cj = cn; shj = shn; chj = chn;
+  }
+  template <int J>
+  __device__ __forceinline__ void series2(const TMercConst &tm) {
+    eps = fma(tm.delta[J], sk, eps);
+    const double sn = sk * cc + ck * sc, cn = ck * cc - sk * sc;
+    sk = sn; ck = cn;
+  }
+  template <int STAGE>
+  __device__ __forceinline__ void step(const TMercConst &tm, double x, double y) {
+    if constexpr (STAGE == 0) {
+      const double dx = x * tm.Ainv;
+      eta = -y * tm.Ainv;
+      ok = fabs(dx) <= 0.0625 && fabs(eta) <= 0.0625;
+      double sd_, cd_;
+      sincos_small(dx, sd_, cd_);
+      s1 = fma(tm.sin_xi0, cd_, tm.cos_xi0 * sd_);
+      c1 = fma(tm.cos_xi0, cd_, -(tm.sin_xi0 * sd_));
+      sinhcosh_small(2 * eta, sh2, ch2);
+    } else if constexpr (STAGE == 1) {
+      s2 = 2 * s1 * c1; c2 = fma(-2 * s1, s1, 1.0);
+      sj = s2; cj = c2; shj = sh2; chj = ch2; dxi = 0; deta = 0;
+      series1<0>(tm);
+    } else if constexpr (STAGE == 2) {
+      series1<1>(tm); series1<2>(tm);
+    } else if constexpr (STAGE == 3) {
+      series1<3>(tm); series1<4>(tm);
+    } else if constexpr (STAGE == 4) {
+      series1<5>(tm);
+      ok = ok && fabs(dxi) <= 0.0625;
+      double shp;
+      sincos_small(dxi, sd, cd);
+      sinhcosh_small(eta - deta, shp, chp);
+    } else if constexpr (STAGE == 5) {
+      const double sxp = s1 * cd - c1 * sd;
+      sch = sxp * fast_rcp(chp);
+    } else if constexpr (STAGE == 6) {
+      const double x2 = fma(-sch, sch, 1.0);        // cos^2(chi) > 0
+      const double y = fast_rsqrt3(x2);
+      double r = x2 * y;
+      r = fma(fma(-r, r, x2), 0.5 * y, r);           // one Newton step on the root: sqrt() to an ulp without its slow-path branch
+      cch = r;
+      sc = 2 * sch * cch; cc = fma(-2 * sch, sch, 1.0);
+      sk = sc; ck = cc; eps = 0;
+    } else if constexpr (STAGE == 7) {
+      series2<0>(tm); series2<1>(tm);
+    } else if constexpr (STAGE == 8) {
+      series2<2>(tm); series2<3>(tm);
+    } else if constexpr (STAGE == 9) {
+      series2<4>(tm); series2<5>(tm);
+      ok = ok && fabs(eps) <= 0.0625;
+    } else if constexpr (STAGE == 10) {
+      double se, ce;
+      sincos_small(eps, se, ce);
+      sin_lat = sch * ce + cch * se;
+      cos_lat = cch * ce - sch * se;
+    }
+  }
+};
+
 // (lat, lon) -> NWU (x, y)   (reference src/PoseUKF.cpp:573 worldToNav)
 __device__ __forceinline__ void tmerc_world_to_nav(const TMercConst &tm, double lat, double lon, double &x, double &y) {
   double tau = tan(lat);

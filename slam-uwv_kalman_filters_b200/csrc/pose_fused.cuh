@@ -35,6 +35,9 @@ constexpr int M_NONE = -1;
 #ifndef UWVKF_TMA_TRAIL           // 1: the interleaved trailing pass reads from a staging buffer filled by one bulk copy per filter
 #define UWVKF_TMA_TRAIL 1
 #endif
+#ifndef UWVKF_TMERC_EARLY         // 1: the predict evaluates the projection of its sigma points INSIDE the panel Cholesky (branch-free, one stage per column from column 1 on): parity green, chol15 grows by what the sigma-point phase loses (the other warps were already filling those slots), 2 % slower, off
+#define UWVKF_TMERC_EARLY 0
+#endif
 #ifndef UWVKF_SHRINK              // 1: predict kernels shrink the panel to 9 columns after the predict's factorisation (FusedCfg::KT): parity green, 2 % slower, off
 #define UWVKF_SHRINK 0
 #endif
@@ -288,8 +291,12 @@ template <int K> constexpr int LStride = K | 1;
 // DFMA), and they replace both the triangular solve G = A L11^-1 and the product G Sigma[:K, :] of the unscented transform:
 //   A L11^-1 Sigma[:K, x] = A (Lp[x, :])^T                       (Sigma[:K, x] = L11 Lp[x, :]^T),
 // i.e. cross-covariances become K-term dot products of registers with broadcast rows of A: no solve, no re-read of Sigma.
-template <int K>
-__device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane, double (&a0)[K], double (&a1)[K]) {
+struct NoHook { __device__ __forceinline__ void col(int, double) const {} };
+// `hook.col(j)` runs once column J of the factor is in shared memory (the predict evaluates its transverse-Mercator projection
+// there, one stage per column from column 1 on: the only sigma points whose position differs from the mean's are those of
+// columns 0 and 1)
+template <int K, class Hook = NoHook>
+__device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane, double (&a0)[K], double (&a1)[K], Hook &&hook = Hook{}) {
   static_assert(K <= 32, "one row per lane");
   constexpr int LS = LStride<K>;
   const int x1 = lane + 32 < N ? lane + 32 : lane;   // lanes without a second row duplicate the first (never consumed)
@@ -309,6 +316,7 @@ __device__ __forceinline__ bool chol_panel(const double *S, double *Lw, int lane
     dg = fma(-a0[j], a0[j], dg);
     if (lane < K) Lw[j * LS + lane] = a0[j];
     __syncwarp();
+    hook.col(j, inv);   // (j is a constant after unrolling: the hook's switch folds away)
     {
       int c = j + 1;
       if (((j * LS + c) & 1) && c < K) {
@@ -949,7 +957,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       // a NaN rotation rate (device-resident control input the host could not scan) would poison the state: the prediction
       // is refused for this filter (status bit), like checkMeasurment() throwing in the reference (src/PoseUKF.cpp:494)
       const bool wbad = isnan(wm_g[0]) || isnan(wm_g[1]) || isnan(wm_g[2]);
+      // Latitude of the sigma points (reference src/PoseUKF.cpp:29-30).  Only the points of columns 0 and 1 of the factor move the
+      // position, so every lane knows its point as soon as those two columns exist.  UWVKF_TMERC_EARLY evaluates the projection
+      // -- one long dependent chain per lane -- there, in stages tied to the columns of the factorisation, hoping to hide one
+      // chain under the other.  Measured: the factorisation grows by exactly what the sigma-point phase loses (3,667 + 3,349 ->
+      // 4,917 + 2,377 cycles per warp) and the kernel is 2 % slower: with three warps per scheduler the slots a waiting warp
+      // leaves are already taken by its neighbours, only removing instructions helps.  Off.
+      double tm_sl = 0.0, tm_cl = 1.0;
+      bool tm_ok = false;
+#if UWVKF_TMERC_EARLY
+      struct TmHook {
+        TMercStages &t; const TMercConst &tm; const double *Lw, *muA; int lane;
+        double px, py;
+        // `tie` makes a stage wait for its column (a true data dependency on the column's 1/sqrt(pivot), times zero): left alone,
+        // ptxas issues the whole projection -- the longest chain in sight -- in one run as soon as column 1 exists, and the
+        // factorisation stands still meanwhile
+        static __device__ __forceinline__ void tie(double &v, double inv) { v = fma(inv, 0.0, v); }
+        __device__ __forceinline__ void col(int j, double inv) {
+          switch (j) {
+            case 1: {
+              const int p = lane, jj = (p - 1) >> 1;
+              const bool on = p > 0 && p < 2 * K + 1;
+              const double sg = (p & 1) ? 1.0 : -1.0;
+              const double d0 = (on && 0 >= jj) ? sg * Lw[jj * LStride<K> + 0] : 0.0;
+              const double d1 = (on && 1 >= jj) ? sg * Lw[jj * LStride<K> + 1] : 0.0;
+              px = muA[P_POS] + d0; py = muA[P_POS + 1] + d1;
+              t.step<0>(tm, px, py);
+            } break;
+            case 2: tie(t.s1, inv); t.step<1>(tm, px, py); break;
+            case 3: tie(t.sj, inv); t.step<2>(tm, px, py); break;
+            case 4: tie(t.sj, inv); t.step<3>(tm, px, py); break;
+            case 5: tie(t.sj, inv); t.step<4>(tm, px, py); break;
+            case 6: tie(t.chp, inv); t.step<5>(tm, px, py); break;
+            case 7: tie(t.sch, inv); t.step<6>(tm, px, py); break;
+            case 8: tie(t.sk, inv); t.step<7>(tm, px, py); break;
+            case 9: tie(t.sk, inv); t.step<8>(tm, px, py); break;
+            case 10: tie(t.sk, inv); t.step<9>(tm, px, py); break;
+            case 11: tie(t.eps, inv); t.step<10>(tm, px, py); break;
+            default: break;
+          }
+        }
+      };
+      TMercStages tms;
+      tms.ok = false; tms.sin_lat = 0.0; tms.cos_lat = 1.0;
+      const bool spd15 = !wbad && chol_panel<K>(SA, Lw, lane, a0, a1, TmHook{tms, P.tm, Lw, muA, lane, 0.0, 0.0});
+      tm_sl = tms.sin_lat; tm_cl = tms.cos_lat; tm_ok = tms.ok;
+#else
       const bool spd15 = !wbad && chol_panel<K>(SA, Lw, lane, a0, a1);
+#endif
       PH(1);
       if (spd15) {
         const Quat q{muA[P_ORI], muA[P_ORI + 1], muA[P_ORI + 2], muA[P_ORI + 3]};
@@ -964,8 +1019,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           double px = muA[P_POS] + d(0), py = muA[P_POS + 1] + d(1);
           Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
           Vec3 wb{wm_g[0] - (muA[P_BG] + d(12)), wm_g[1] - (muA[P_BG + 1] + d(13)), wm_g[2] - (muA[P_BG + 2] + d(14))};
-          double sl, cl;
+          double sl = tm_sl, cl = tm_cl;
+#if UWVKF_TMERC_EARLY
+          if (!tm_ok) tmerc_nav_to_sincos_lat(P.tm, px, py, sl, cl);   // far from the projection origin: generic routines
+#elif defined(UWVKF_EXP_NOTMERC)
+          sl = P.tm.sin_xi0 + 1e-7 * px; cl = P.tm.cos_xi0 + 1e-7 * py;   // experiment (WRONG results): what the projection costs
+#else
           tmerc_nav_to_sincos_lat(P.tm, px, py, sl, cl);
+#endif
           Vec3 wn = qrot(qq, wb);
           wn.x -= kEarthW * cl;
           wn.z -= kEarthW * sl;
