@@ -132,6 +132,46 @@ def test_config3_pose_ukf_full_state_262144(pkg, syn):
     ukf.close()
 
 
+def test_headline_1m_filters_host_step(pkg, syn):
+    """The headline workload at its full size (BASELINE metric: 1,048,576 PoseUKF filters on one GPU, fused predictionStep +
+    integrateMeasurement(Velocity)) through the host-buffer entry point `bench.py` times as e2e (uwvkf_pose_step_host): a sample
+    of filters spread over the batch against the free-running oracle, and size-independent properties of the whole batch."""
+    import torch
+    B, STEPS = 1 << 20, 6
+    ukf, cfg, par, Q, cov0 = _pose_batch(pkg, syn, B)
+    smp = _sample(B, 5)
+    omu, _ = syn.pose_initial_batch(smp, cfg, with_cov=False)
+    ocov = np.tile(cov0, (len(smp), 1, 1))
+    off = np.concatenate([omu[:, 20:47], omu[:, 53:54]], axis=1)
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    ring = [(pin((B, 3)), pin((B, 3))) for _ in range(2)]
+    navs = [pin((B, 10)) for _ in range(3)]
+    for s in range(1, STEPS + 1):
+        inp = _pose_inputs(syn, 0, B, s)
+        g, z = ring[s % 2]
+        g[:] = inp["gyro"]; z[:] = inp["dvl"]
+        ukf.step_host(DT, g, pkg.POSE_VELOCITY, z, syn.R_DVL, nav_out=navs[s % 3])
+        for k, f in enumerate(smp):
+            w = inp["gyro"][f]
+            omu[k], ocov[k], st, _ = orc.pose_predict(omu[k], ocov[k], Q, w, par, off[k], DT)
+            omu[k], ocov[k], st, _ = orc.pose_update(orc.VELOCITY, omu[k], ocov[k], inp["dvl"][f], syn.R_DVL, None, w, par)
+            assert st == 0
+    ukf.synchronize()
+    assert not ukf.get_status().any()
+    errs = np.zeros(4)
+    for k, f in enumerate(smp):
+        gm, gc = ukf.get_state(first=int(f), count=1)
+        errs = np.maximum(errs, all_errs(gm[0], gc[0], omu[k], ocov[k]))
+        assert np.array_equal(gc[0], gc[0].T) and np.linalg.eigvalsh(gc[0]).min() > 0
+    _gate(errs, f"[headline] {B} filters x {STEPS} fused host steps, free-running sample")
+    nav = navs[STEPS % 3]                                 # written by the fused kernel itself, downloaded on the copy stream
+    assert np.array_equal(nav, ukf.get_navigation())
+    assert np.isfinite(nav).all() and np.abs(np.linalg.norm(nav[:, 3:7], axis=1) - 1).max() < 1e-12
+    stats = ukf.ensemble_stats()
+    assert stats[0] == B and np.allclose(stats[1:11], nav.sum(0), rtol=1e-11, atol=1e-6)
+    ukf.close()
+
+
 def test_config4_adcp_dropouts_monte_carlo_shard(pkg, syn):
     """config 4: PoseUKF with ADCP aiding and DVL dropouts, Monte-Carlo sweep (per-filter DVL noise multipliers); one
     131,072-filter shard of the 1M-filter job (= what each of 8 GPUs owns), and shard invariance against a second,
