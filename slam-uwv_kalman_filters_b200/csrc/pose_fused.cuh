@@ -1570,7 +1570,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
     // =================================== write back ===========================================================
     PH(27);
     // navigation solution of the pipelined host step: the first ten stored doubles of mu, whatever happened to the filter
-    if (a.nav != nullptr && lane < 10) __stcs(a.nav + f * 10 + lane, mu[lane]);
+    if constexpr (HAS_PREDICT) {   // (the host step always predicts; the update-only kernels stay as they were: 4 % each, register allocation)
+      if (a.nav != nullptr && lane < 10) __stcs(a.nav + f * 10 + lane, mu[lane]);
+    }
     if (predicted || updated) {
       {
         double2 *dst = reinterpret_cast<double2 *>(blk);
