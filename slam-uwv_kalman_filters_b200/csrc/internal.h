@@ -44,6 +44,7 @@ struct uwvkf_filter_s {
   double *d_state = nullptr, *d_offsets = nullptr, *d_rot = nullptr, *d_Q = nullptr, *d_uwv = nullptr;
   uwvkf::pose::Params pp{};
   bool have_params = false, have_Q = false;
+  double *d_tm = nullptr;        // [B][10]: latitudes of the predict's sigma points (pose_tmerc_prepass_kernel)
   double *nav_fused = nullptr;   // set around the fused launch of uwvkf_pose_step_host: the kernel writes the navigation solution itself
   // uwvkf_pose_step_host: two input slots / two navigation buffers, upload and download streams, events per slot
   struct HostPipe {

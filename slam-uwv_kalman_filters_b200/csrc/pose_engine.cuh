@@ -69,6 +69,8 @@ struct Launch {
   const double *uwv;       // NUWV doubles (motion-model parameters of the constructor, src/PoseUKF.cpp:353-354) or nullptr
   double *nav;             // [B][10] or nullptr: the fused kernel also writes p(3) q(4) v(3) of every filter after the step (the
                            // navigation read-back of uwvkf_pose_step_host without a second kernel and a second pass over mu)
+  const double *tm;        // [B][10] or nullptr: sin / cos of the latitude of the five distinct sigma-point positions of the predict,
+                           // written by pose_tmerc_prepass_kernel right before this launch (pose_fused.cuh, UWVKF_TMERC_PREPASS)
   long long B;
   int nops;
   Op ops[3];

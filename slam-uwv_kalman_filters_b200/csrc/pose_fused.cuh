@@ -35,6 +35,9 @@ constexpr int M_NONE = -1;
 #ifndef UWVKF_TMA_TRAIL           // 1: the interleaved trailing pass reads from a staging buffer filled by one bulk copy per filter
 #define UWVKF_TMA_TRAIL 1
 #endif
+#ifndef UWVKF_TMERC_PREPASS       // 1: the latitudes of the predict's sigma points come from a thread-per-filter pre-pass kernel (32 filters per warp instruction instead of one)
+#define UWVKF_TMERC_PREPASS 1
+#endif
 #ifndef UWVKF_TMERC_EARLY         // 1: the predict evaluates the projection of its sigma points INSIDE the panel Cholesky (branch-free, one stage per column from column 1 on): parity green, chol15 grows by what the sigma-point phase loses (the other warps were already filling those slots), 2 % slower, off
 #define UWVKF_TMERC_EARLY 0
 #endif
@@ -193,7 +196,9 @@ struct FusedCfg {
   static constexpr int O_LT = O_KC + KCW * 54;         // rows T of the panel factor, NT x KE
   // per-filter inputs staged with the prefix: rotation rate [0..2], z [4..4+M), z of the second update [8..8+M2); two sets,
   // alternating per filter (the next filter's inputs arrive while the current filter's update still reads its own)
-  static constexpr int INW = (KIND2 == M_NONE) ? 8 : 12;
+  static constexpr int INB = (KIND2 == M_NONE) ? 8 : 12;              // rotation rate and measurement slots
+  static constexpr bool TMP = UWVKF_TMERC_PREPASS && HAS_PREDICT;    // + sin / cos of the latitude of sigma points 0..4 (pre-pass)
+  static constexpr int INW = INB + (TMP ? 10 : 0);
   static constexpr int O_IN = O_LT + NT * KE;
   static constexpr int O_MB = O_IN + 2 * INW;      // mbarriers of the bulk (TMA) copies: [0] prefix fetch, [1] trailing triangle
   // The interleaved trailing pass reads the old trailing triangle from a shared-memory STAGING buffer that ONE bulk copy fills at
@@ -755,6 +760,37 @@ __device__ inline double markov_rate(int s, const Params &P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Latitude of the predict's sigma points (reference src/PoseUKF.cpp:29-30), ONE THREAD PER FILTER.  A sigma point's position differs
+// from the mean's only for the points of columns 0 and 1 of the Cholesky factor (column j moves the coordinates >= j), so a filter
+// has five distinct positions: (x, y), (x +- L00, y +- L10), (x, y +- L11).  Inside the fused kernel every lane evaluates the
+// projection of its own point -- a warp instruction per operation for ONE filter, ~290 of the kernel's 5,050 instructions; here a
+// warp instruction serves 32 filters and evaluates all five.  The three factor entries are computed with the very operations of
+// chol_panel (same seed, same Newton step, same FMA), so the positions are the doubles the fused kernel would form itself.
+// out[f][2 p], out[f][2 p + 1] = sin, cos of the latitude of sigma point p = 0..4; the fused kernel stages them with its inputs.
+__global__ void __launch_bounds__(256) pose_tmerc_prepass_kernel(const double *__restrict__ state, double *__restrict__ out, long long B,
+                                                                 const __grid_constant__ Params P) {
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  const double *blk = state + f * BLK;
+  const double2 xy = *reinterpret_cast<const double2 *>(blk + P_POS);
+  const double2 s0 = *reinterpret_cast<const double2 *>(blk + OFF_S);            // Sigma00, Sigma10
+  const double s11 = blk[OFF_S + cidx(1, 1)];
+  const double inv0 = fast_rsqrt3(s0.x);
+  const double l00 = s0.x * inv0, l10 = s0.y * inv0;
+  const double d1 = fma(-l10, l10, s11);
+  const double l11 = d1 * fast_rsqrt3(d1);
+  double2 *o = reinterpret_cast<double2 *>(out + f * 10);
+#pragma unroll 1
+  for (int p = 0; p < 5; ++p) {
+    const double sg = (p & 1) ? 1.0 : -1.0;
+    const double d0 = (p == 1 || p == 2) ? sg * l00 : 0.0;
+    const double dy = (p == 1 || p == 2) ? sg * l10 : (p >= 3 ? sg * l11 : 0.0);
+    double sl, cl;
+    tmerc_nav_to_sincos_lat(P.tm, xy.x + d0, xy.y + dy, sl, cl);
+    o[p] = make_double2(sl, cl);
+  }
+}
+
 template <int HAS_PREDICT, int KIND, int WARPS, int KIND2 = M_NONE>
 __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, const __grid_constant__ Params P) {
   using C = FusedCfg<HAS_PREDICT, KIND, KIND2>;
@@ -852,6 +888,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(opu.z + ff * C::MF::M + (lane - 4)) : "memory");
     if (KIND2 != M_NONE && lane >= 8 && lane < 8 + C::MF2::M)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ina + 8u * lane), "l"(opu2.z + ff * C::MF2::M + (lane - 8)) : "memory");
+    if (C::TMP && lane >= 16 && lane < 21)   // (sin, cos) of the latitude of sigma point lane - 16, from the pre-pass kernel
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ina + 8u * (C::INB + 2 * (lane - 16))),
+                   "l"(a.tm + ff * 10 + 2 * (lane - 16)) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   {
@@ -1020,7 +1059,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pose_fused_kernel(Launch a, con
           Quat qq = so3_boxplus(q, Vec3{d(3), d(4), d(5)}, 1.0);
           Vec3 wb{wm_g[0] - (muA[P_BG] + d(12)), wm_g[1] - (muA[P_BG + 1] + d(13)), wm_g[2] - (muA[P_BG + 2] + d(14))};
           double sl = tm_sl, cl = tm_cl;
-#if UWVKF_TMERC_EARLY
+#if UWVKF_TMERC_PREPASS
+          {   // only the points of columns 0 and 1 of the factor (p = 1..4) sit at a position of their own
+            const double2 t2 = *reinterpret_cast<const double2 *>(inb + C::INB + 2 * (p < 5 ? p : 0));
+            sl = t2.x; cl = t2.y;
+            (void)px; (void)py; (void)tm_ok;
+          }
+#elif UWVKF_TMERC_EARLY
           if (!tm_ok) tmerc_nav_to_sincos_lat(P.tm, px, py, sl, cl);   // far from the projection origin: generic routines
 #elif defined(UWVKF_EXP_NOTMERC)
           sl = P.tm.sin_xi0 + 1e-7 * px; cl = P.tm.cos_xi0 + 1e-7 * py;   // experiment (WRONG results): what the projection costs

@@ -434,6 +434,12 @@ int launch_fused(uwvkf_handle h, const pose::Launch &L) {
   }
   long long need = (L.B + WARPS - 1) / WARPS;
   int grid = (int)std::min<long long>(need, h->sm_count);
+  if constexpr (C::TMP) {
+    // latitudes of the predict's sigma points, thread per filter, on the same stream right ahead of the fused kernel
+    pose::pose_tmerc_prepass_kernel<<<(unsigned)((L.B + 255) / 256), 256, 0, h->stream>>>(L.state, h->d_tm, L.B, h->pp);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
   pose::pose_fused_kernel<HP, KIND, WARPS, KIND2><<<grid, WARPS * 32, smem, h->stream>>>(L, h->pp);
   CK(cudaGetLastError());
   h->launches++;
@@ -461,6 +467,7 @@ int run_pose(uwvkf_handle h, int nops, const pose::Op *ops) {
   L.state = h->d_state; L.offsets = h->d_offsets; L.rot_rate = h->d_rot; L.status = h->d_status; L.Q = h->d_Q;
   L.uwv = h->d_uwv;
   L.nav = h->nav_fused;
+  L.tm = h->d_tm;
   L.B = h->B; L.nops = nops;
   bool slow = false, dense_only = false, full_efforts = false;
   for (int o = 0; o < nops; ++o) {
@@ -600,6 +607,9 @@ int uwvkf_create(int filter_kind, int64_t batch, int device, uwvkf_handle *out) 
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_state, (size_t)batch * pose::BLK * sizeof(double));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_offsets, (size_t)batch * pose::NOFF * sizeof(double));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_rot, (size_t)batch * 3 * sizeof(double));
+#if UWVKF_TMERC_PREPASS
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_tm, (size_t)batch * 10 * sizeof(double));   // written before it is read, every predict
+#endif
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_status, (size_t)batch * sizeof(uint32_t));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_Q, (size_t)pose::NP * sizeof(double));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_state, 0, (size_t)batch * pose::BLK * sizeof(double));
@@ -641,7 +651,7 @@ static void destroy_pipe(uwvkf_handle h) {
 int uwvkf_destroy(uwvkf_handle h) {
   if (!h) return UWVKF_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_status); cudaFree(h->d_Q);
+  cudaFree(h->d_state); cudaFree(h->d_offsets); cudaFree(h->d_rot); cudaFree(h->d_tm); cudaFree(h->d_status); cudaFree(h->d_Q);
   cudaFree(h->d_z); cudaFree(h->d_Rpf); cudaFree(h->d_valid); cudaFree(h->d_tmp); cudaFree(h->d_uwv);
   cudaFree(h->d_z2); cudaFree(h->d_valid2);
   destroy_pipe(h);

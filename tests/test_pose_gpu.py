@@ -609,7 +609,7 @@ def test_cuda_graph_replay_of_a_schedule(pkg, syn, scen):
     a.graph_launch(g)
     a.graph_launch(g)
     a.synchronize()
-    assert a.kernel_launches == n0 + 2 * 2 * K + 1      # 2 replays x (fused step + update) x K, + the getter above
+    assert a.kernel_launches == n0 + 2 * 3 * K + 1      # 2 replays x (latitude pre-pass + fused step + update) x K, + the getter above
     ma, ca = a.get_state()
     mb, cb = b.get_state()
     assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
