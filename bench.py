@@ -28,8 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 DT = 0.01
 B_ALG = 23760.0          # algorithmic HBM bytes per filter-step: read + write of mu (54) and packed Sigma (1431) doubles
 W_ALG = 1.0e6            # FP64 flop per filter-step of the REFERENCE algorithm (symmetric-minimal count)
-W_EXEC = 1.518e5         # FP64 flop per filter-step the fused kernel executes (ncu: 32 x (2 x 1507 DFMA + 553 DMUL + 122 DADD) + 512 x
-                         # 66 DMMA, profiles/r2_pose_fused_kernel_1M.txt): the prefix-structured transform does 7x less arithmetic
+W_EXEC = 1.441e5         # FP64 flop per filter-step executed (final round-2 ncu capture: 32 x (2 x 1395 DFMA + 485 DMUL + 125 DADD) + 512 x
+                         # 66 DMMA in the fused kernel = 1.426e5, + ~1.5e3 in the thread-per-filter latitude pre-pass)
 FP64_PEAK = 36.9e12      # measured DFMA peak of this pool's B200 (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)
 METRIC = "PoseUKF predict+update filter-steps/sec"
 UNIT = "filter-steps/s"
@@ -288,7 +288,7 @@ def main():
                 "data": "synthetic",
                 "config": our_config(B, world, NR),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "pose_fused_kernel<predict, DVL update, 12 warps>",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "pose_fused_kernel<predict, DVL update, 12 warps> (kernel_ms is the whole step: the thread-per-filter latitude pre-pass, ~1 % of it, is not subtracted)",
                              "traffic_source": traffic_src,
                              "kernel_ms": kern_ms, "alg_bytes_per_filter_step": B_ALG,
                              "fp64": {"executed_tflops": W_EXEC * B / (kern_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK / 1e12,
