@@ -1,3 +1,5 @@
+# tools/final_capture.sh (GPU box): the measurement set behind profiles/: bench line, per-op and config timings, launch list, one ncu --set full capture of the fused kernel.
+# Every ncu pass runs only after the same command has exited 0 without ncu; outputs land in gpurun_out/ (copy the summaries into profiles/ with profiles/analyze.py).
 set -x
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_1gpu.json 2> gpurun_out/r2f_bench.err || exit 1
 python tools/bench_ops.py --out gpurun_out/r2f_ops.json > gpurun_out/r2f_ops.log 2>&1
